@@ -1,0 +1,234 @@
+"""Deterministic synthetic parameters for the ROMP hot path.
+
+The released checkpoint (``ROMP.pkl``) and the licensed SMPL model file are not
+available offline, so the benchmarks and parity tests run on seeded synthetic
+parameters that have exactly the reference's schema:
+
+* ``romp_state_dict(seed)``  -> dict with the 1851 keys / shapes of
+  ``ROMPv1().state_dict()`` (reference: simple_romp/romp/model.py:420-481).
+* ``smpl_pack(seed)``        -> dict with the keys written by
+  simple_romp/romp/pack_smpl_info.py:70-111 and read by
+  simple_romp/romp/smpl.py:41-59.
+
+Everything is drawn from ``numpy.random.RandomState`` so the values do not depend
+on the torch version.  BatchNorm statistics are randomised so that BN folding is
+really exercised.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# --------------------------------------------------------------------------------------
+# HRNet-W32 + ROMP head parameter enumeration (names and shapes only)
+# --------------------------------------------------------------------------------------
+STAGE_CFG = {
+    2: dict(modules=1, channels=[32, 64]),
+    3: dict(modules=4, channels=[32, 64, 128]),
+    4: dict(modules=3, channels=[32, 64, 128, 256]),
+}
+BLOCKS_PER_BRANCH = 4
+HEAD_OUT = {1: 142, 2: 1, 3: 3}   # final_layers index -> output channels (params, center, cam)
+
+
+def _conv(specs, name, cout, cin, k, bias=False):
+    specs.append((name + ".weight", (cout, cin, k, k), "conv_w"))
+    if bias:
+        specs.append((name + ".bias", (cout,), "conv_b", cin * k * k))
+
+
+def _bn(specs, name, c):
+    specs.append((name + ".weight", (c,), "bn_w"))
+    specs.append((name + ".bias", (c,), "bn_b"))
+    specs.append((name + ".running_mean", (c,), "bn_m"))
+    specs.append((name + ".running_var", (c,), "bn_v"))
+    specs.append((name + ".num_batches_tracked", (), "bn_n"))
+
+
+def romp_param_specs():
+    """Ordered (name, shape, kind, ...) list equal to ROMPv1().state_dict() order."""
+    s = []
+    p = "backbone."
+    _conv(s, p + "conv1", 64, 3, 3); _bn(s, p + "bn1", 64)
+    _conv(s, p + "conv2", 64, 64, 3); _bn(s, p + "bn2", 64)
+    # layer1: 4 Bottlenecks, first has a 1x1 downsample 64->256
+    for i in range(4):
+        q = f"{p}layer1.{i}."
+        cin = 64 if i == 0 else 256
+        _conv(s, q + "conv1", 64, cin, 1); _bn(s, q + "bn1", 64)
+        _conv(s, q + "conv2", 64, 64, 3); _bn(s, q + "bn2", 64)
+        _conv(s, q + "conv3", 256, 64, 1); _bn(s, q + "bn3", 256)
+        if i == 0:
+            _conv(s, q + "downsample.0", 256, 64, 1); _bn(s, q + "downsample.1", 256)
+    # transition1: [256] -> [32, 64]
+    _conv(s, p + "transition1.0.0", 32, 256, 3); _bn(s, p + "transition1.0.1", 32)
+    _conv(s, p + "transition1.1.0.0", 64, 256, 3); _bn(s, p + "transition1.1.0.1", 64)
+
+    def stage(idx):
+        cfg = STAGE_CFG[idx]
+        ch = cfg["channels"]
+        nb = len(ch)
+        for m in range(cfg["modules"]):
+            q = f"{p}stage{idx}.{m}."
+            for b in range(nb):
+                for k in range(BLOCKS_PER_BRANCH):
+                    r = f"{q}branches.{b}.{k}."
+                    _conv(s, r + "conv1", ch[b], ch[b], 3); _bn(s, r + "bn1", ch[b])
+                    _conv(s, r + "conv2", ch[b], ch[b], 3); _bn(s, r + "bn2", ch[b])
+            multi = not (idx == 4 and m == cfg["modules"] - 1)
+            for i in range(nb if multi else 1):
+                for j in range(nb):
+                    r = f"{q}fuse_layers.{i}.{j}."
+                    if j > i:
+                        _conv(s, r + "0", ch[i], ch[j], 1); _bn(s, r + "1", ch[i])
+                    elif j < i:
+                        for k in range(i - j):
+                            cout = ch[i] if k == i - j - 1 else ch[j]
+                            _conv(s, f"{r}{k}.0", cout, ch[j], 3); _bn(s, f"{r}{k}.1", cout)
+
+    stage(2)
+    _conv(s, p + "transition2.2.0.0", 128, 64, 3); _bn(s, p + "transition2.2.0.1", 128)
+    stage(3)
+    _conv(s, p + "transition3.3.0.0", 256, 128, 3); _bn(s, p + "transition3.3.0.1", 256)
+    stage(4)
+    for h in (1, 2, 3):
+        q = f"final_layers.{h}."
+        _conv(s, q + "0.0", 64, 34, 3, bias=True); _bn(s, q + "0.1", 64)
+        for blk in range(2):
+            r = f"{q}1.{blk}.0."
+            _conv(s, r + "conv1", 64, 64, 3); _bn(s, r + "bn1", 64)
+            _conv(s, r + "conv2", 64, 64, 3); _bn(s, r + "bn2", 64)
+        _conv(s, q + "2", HEAD_OUT[h], 64, 1, bias=True)
+    return s
+
+
+def romp_state_dict(seed: int = 0, gain: float = 0.55):
+    """Synthetic ROMPv1 state dict as numpy arrays (float32 / int64 scalars)."""
+    rng = np.random.RandomState(seed)
+    sd = {}
+    for spec in romp_param_specs():
+        name, shape, kind = spec[0], spec[1], spec[2]
+        if kind == "conv_w":
+            fan_in = shape[1] * shape[2] * shape[3]
+            bound = gain * np.sqrt(3.0 / fan_in)          # unit-variance-preserving uniform
+            v = rng.uniform(-bound, bound, size=shape)
+        elif kind == "conv_b":
+            bound = 1.0 / np.sqrt(spec[3])
+            v = rng.uniform(-bound, bound, size=shape)
+        elif kind == "bn_w":
+            v = rng.uniform(0.5, 1.5, size=shape)
+        elif kind == "bn_b":
+            v = rng.normal(0.0, 0.1, size=shape)
+        elif kind == "bn_m":
+            v = rng.normal(0.0, 0.1, size=shape)
+        elif kind == "bn_v":
+            v = rng.uniform(0.5, 1.5, size=shape)
+        elif kind == "bn_n":
+            sd[name] = np.array(1, dtype=np.int64)
+            continue
+        else:  # pragma: no cover
+            raise ValueError(kind)
+        sd[name] = v.astype(np.float32)
+    return sd
+
+
+# --------------------------------------------------------------------------------------
+# Synthetic packed SMPL (schema: simple_romp/romp/pack_smpl_info.py:70-111)
+# --------------------------------------------------------------------------------------
+SMPL_PARENTS = np.array([-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14,
+                         16, 17, 18, 19, 20, 21], dtype=np.int64)
+NUM_VERTS = 6890
+NUM_FACES = 13776
+
+
+def smpl_pack(seed: int = 0, num_betas: int = 10, dense_weights: bool = False):
+    """Synthetic packed SMPL with human-like magnitudes.
+
+    v_template ~ a 1.7 m tall point cloud, shapedirs ~ cm scale, posedirs ~ mm-cm scale,
+    skinning weights with 4 non-zeros per vertex (or dense if ``dense_weights``) that sum to 1,
+    joint regressors as sparse convex combinations (stored dense like the reference).
+    """
+    rng = np.random.RandomState(seed + 7919)
+    V = NUM_VERTS
+    v_template = (rng.uniform(-1, 1, size=(V, 3)) * np.array([0.45, 0.85, 0.15])).astype(np.float32)
+    shapedirs = (rng.normal(0, 0.01, size=(V, 3, num_betas))).astype(np.float32)
+    posedirs = (rng.normal(0, 0.004, size=(207, V * 3))).astype(np.float32)
+
+    def convex_rows(rows, nnz):
+        m = np.zeros((rows, V), dtype=np.float64)
+        for r in range(rows):
+            idx = rng.choice(V, size=nnz, replace=False)
+            w = rng.uniform(0.1, 1.0, size=nnz)
+            m[r, idx] = w / w.sum()
+        return m.astype(np.float32)
+
+    J_regressor = convex_rows(24, 48)
+    J_extra9 = convex_rows(9, 32)
+    J_h36m17 = convex_rows(17, 64)
+    if dense_weights:
+        w = rng.uniform(0.0, 1.0, size=(V, 24)) ** 4
+    else:
+        w = np.zeros((V, 24), dtype=np.float64)
+        for v in range(V):
+            idx = rng.choice(24, size=4, replace=False)
+            w[v, idx] = rng.uniform(0.05, 1.0, size=4)
+    weights = (w / w.sum(1, keepdims=True)).astype(np.float32)
+    extra_joints_index = rng.choice(V, size=21, replace=False).astype(np.int64)
+    faces = rng.randint(0, V, size=(NUM_FACES, 3)).astype(np.int64)
+    key = "shapedirs" if num_betas == 10 else "smpla_shapedirs"
+    pack = {
+        "kintree_table": SMPL_PARENTS.copy(),
+        "J_regressor_extra9": J_extra9,
+        "J_regressor_h36m17": J_h36m17,
+        key: shapedirs,
+        "posedirs": posedirs,
+        "extra_joints_index": extra_joints_index,
+        "f": faces,
+        "v_template": v_template,
+        "J_regressor": J_regressor,
+        "weights": weights,
+    }
+    if num_betas != 10:
+        pack["shapedirs"] = shapedirs[:, :, :10].copy()
+    return pack
+
+
+def synthetic_frames(batch: int, seed: int = 0, dtype=np.uint8):
+    """[B,512,512,3] frames with values 0..255 (what img_preprocess produces, utils.py:26-30)."""
+    rng = np.random.RandomState(seed + 104729)
+    # low-frequency structure + noise so activations are not pure white noise
+    base = rng.randint(0, 256, size=(batch, 64, 64, 3)).astype(np.float32)
+    up = np.repeat(np.repeat(base, 8, axis=1), 8, axis=2)
+    noise = rng.randint(-32, 33, size=(batch, 512, 512, 3)).astype(np.float32)
+    x = np.clip(up + noise, 0, 255)
+    return x.astype(dtype)
+
+
+def plant_centers(batch: int, seed: int = 0, kmin: int = 1, kmax: int = 10, size: int = 64):
+    """Center maps [B,1,size,size] with K_b ~ U{kmin..kmax} isolated peaks per frame.
+
+    Peaks are >=3 cells apart (5x5 NMS keeps them all) and have distinct values in (0.3, 1.0)
+    so that the top-k order has no ties.
+    Returns (maps float32, list of per-frame [(flat_index, value)] sorted by value desc).
+    """
+    rng = np.random.RandomState(seed + 15485863)
+    maps = np.zeros((batch, 1, size, size), dtype=np.float32)
+    truth = []
+    for b in range(batch):
+        k = rng.randint(kmin, kmax + 1)
+        cells = []
+        tries = 0
+        while len(cells) < k and tries < 10000:
+            tries += 1
+            y, x = rng.randint(0, size), rng.randint(0, size)
+            if all(max(abs(y - cy), abs(x - cx)) >= 3 for cy, cx in cells):
+                cells.append((y, x))
+        vals = rng.uniform(0.3, 1.0, size=len(cells)).astype(np.float32)
+        vals = np.unique(vals)[: len(cells)]
+        rng.shuffle(vals)
+        cur = []
+        for (y, x), v in zip(cells, vals):
+            maps[b, 0, y, x] = v
+            cur.append((y * size + x, float(v)))
+        cur.sort(key=lambda t: -t[1])
+        truth.append(cur)
+    return maps, truth
