@@ -1,0 +1,154 @@
+/*
+ * b200romp.h - C ABI of libb200romp.so: the B200 (sm_100a) implementation of ROMP's per-frame
+ * inference hot path.
+ *
+ * The reference (Arthur151/ROMP, simple_romp) has no FFI on this path: it is a Python class API whose
+ * four internal seams call PyTorch ops.  Each entry point below replaces one
+ * seam; the reference file:line it stands in for is cited next to it.  All pointers are plain device
+ * (or, where noted, host) pointers, all sizes are ints, nothing torch-typed crosses the boundary.
+ * Every call enqueues work on the caller's CUDA stream and returns immediately; the caller owns all
+ * input/output buffers; the library owns only packed constants and the conv-graph workspace.
+ *
+ * Return convention: 0 = OK, negative = error (b200romp_last_error() gives the text).  "Nobody
+ * detected" is NOT an error: the person count simply comes back as 0 (reference: post_parser.py:138-140).
+ * There is no CPU fallback anywhere in this library.
+ */
+#ifndef B200ROMP_H_
+#define B200ROMP_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200ROMP_VERSION 100
+
+enum { B200ROMP_OK = 0, B200ROMP_EINVAL = -1, B200ROMP_ECUDA = -2, B200ROMP_ENOMEM = -3, B200ROMP_ESTATE = -4 };
+enum { B200ROMP_F32 = 0, B200ROMP_BF16 = 1, B200ROMP_U8 = 2 };
+/* conv engines */
+enum { B200ROMP_ENGINE_AUTO = 0, B200ROMP_ENGINE_SIMT = 1, B200ROMP_ENGINE_TCGEN05 = 2 };
+
+typedef struct b200romp_net b200romp_net;    /* a conv graph: backbone + heads                          */
+typedef struct b200romp_smpl b200romp_smpl;  /* packed SMPL constants                                     */
+typedef void* b200romp_stream;               /* cudaStream_t                                              */
+
+int b200romp_version(void);
+const char* b200romp_last_error(void);
+/* number of SMs / compute capability of the current device, -1 on error (used to size persistent grids) */
+int b200romp_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------------
+ * Seam S1: `center_maps, params_maps = self.model(image)`  (simple_romp/romp/main.py:112;
+ * ROMPv1.forward model.py:470-481; HigherResolutionNet.forward model.py:382-417).
+ *
+ * The model is handed over as a graph of fused conv ops on NHWC activation tensors (BatchNorm already
+ * folded into weight/bias by the host layer, which reads the reference's state-dict keys).
+ * One op computes, for every output pixel p and channel c,
+ *     v = sum_{tap,ci} W[c][ci][tap] * in[p*stride + tap - pad][in_c_off + ci] + bias[c]
+ *     for each (dy,dx) in the upsample x upsample block of p:   (nearest upsample, model.py:197)
+ *         o = v + res[...]            (residual / running fuse sum, model.py:80,239-241)
+ *         o = relu ? max(o,0) : o     (model.py:81,242)
+ *         o = (c == pow_channel) ? 1.1**o : o        (main.py:113)
+ *         out[..][out_c_off + c] = o
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct b200romp_conv_desc {
+  int in, in_c_off;        /* input tensor id, first input channel                                      */
+  int out, out_c_off;      /* output tensor id, first output channel                                    */
+  int res, res_c_off;      /* residual tensor id or -1, first residual channel                          */
+  int res_broadcast;       /* 1 = residual has no batch dimension (per-pixel bias map)                  */
+  int cin, cout;           /* channels consumed / produced                                              */
+  int ksize, stride;       /* 1|3, 1|2 (padding = ksize/2)                                              */
+  int relu;                /* 1 = ReLU after the residual add                                           */
+  int upsample;            /* 1, 2, 4, 8: nearest-neighbour replication of each conv output             */
+  int input_norm;          /* 1 = input tensor holds raw 0..255 frames: x/255*2-1 on load (model.py:384) */
+  int pow_channel;         /* output channel (before out_c_off) that gets 1.1**x, or -1                 */
+  int engine;              /* B200ROMP_ENGINE_*                                                          */
+} b200romp_conv_desc;
+
+b200romp_net* b200romp_net_create(int device);
+void b200romp_net_destroy(b200romp_net* net);
+/* Declares a per-frame tensor [H,W,C] (NHWC; `nchw`=1 declares [C,H,W], only valid for fp32 outputs).
+ * `external`=1: the buffer is caller-owned and bound with b200romp_net_bind before each run.
+ * Returns the tensor id (>=0) or a negative error. */
+int b200romp_net_add_tensor(b200romp_net* net, int H, int W, int C, int dtype, int nchw, int external);
+/* Constant [H,W,C] tensor without batch dimension, uploaded now (e.g. the coord-conv bias map that
+ * replaces `torch.cat((x, coordmaps))`, model.py:473). */
+int b200romp_net_add_const_tensor(b200romp_net* net, int H, int W, int C, int dtype, const void* host_data);
+/* weight: host fp32 [cout][cin][k][k] (PyTorch OIHW), bias: host fp32 [cout] or NULL. Returns op id. */
+int b200romp_net_add_conv(b200romp_net* net, const b200romp_conv_desc* desc, const float* weight, const float* bias);
+/* Packs weights for the chosen engines, uploads them, plans buffer reuse and allocates the workspace. */
+int b200romp_net_finalize(b200romp_net* net, int max_batch);
+int b200romp_net_bind(b200romp_net* net, int tensor, void* device_ptr);
+/* Enqueue the whole graph for `batch` frames on `stream` (replays a cached CUDA graph when possible). */
+int b200romp_net_run(b200romp_net* net, int batch, b200romp_stream stream);
+/* Debug/validation: copy an internal tensor ([batch,H,W,C] in its own dtype) to a device buffer. */
+int b200romp_net_read_tensor(b200romp_net* net, int tensor, int batch, void* dst_device, b200romp_stream stream);
+/* Text description of the plan (one line per op: engine, shapes, buffers); returns bytes written. */
+int b200romp_net_describe(b200romp_net* net, char* buf, int len);
+/* Number of kernels one b200romp_net_run launches (gpu_launches accounting in bench.py). */
+int b200romp_net_num_launches(b200romp_net* net);
+/* workspace bytes currently held */
+long long b200romp_net_workspace_bytes(b200romp_net* net);
+
+/* Stand-alone conv op on caller buffers (kernel unit tests / microbenchmarks).  Tensors are
+ * [batch,H,W,C]; weights as in add_conv. `in_dtype`/`out_dtype`/`res_dtype` are B200ROMP_* codes. */
+int b200romp_conv2d(const b200romp_conv_desc* desc, const float* weight_host, const float* bias_host,
+                    const void* in, int in_dtype, int in_H, int in_W, int in_C,
+                    void* out, int out_dtype, int out_C, int out_nchw,
+                    const void* res, int res_dtype, int batch, b200romp_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Seam S2: `parsing_outputs(center_maps, params_maps, parser)` (post_parser.py:135-146):
+ * CenterMap.parse_centermap (:27-47: 5x5 max-pool NMS :50-54, top-64, threshold), parameter_sampling
+ * (:128-133), pack_params_dict (:66-79) incl. rot6D_to_angular (utils.py:471-682).
+ * center_maps [B,1,S,S] fp32, params_maps [B,P,S,S] fp32 (channel 0 already 1.1**x).
+ * Outputs are written for persons 0..N-1 in (frame asc, score desc; ties: flat index asc) order,
+ * N = min(*d_count, capacity); rows >= N are left untouched.
+ *   d_count[1] i32 | batch_ids[cap] i64 | flat_inds[cap] i64 | center_confs[cap] f32 |
+ *   params_pred[cap,P] f32 | cam[cap,3] | thetas[cap,72] (6 trailing zeros) | betas[cap,n_betas] |
+ *   center_preds[cap,2] i64 = (x,y)*512//S
+ * P = 3 + 22*6 + n_betas.  `thresh` must be >= 0 (with a negative threshold the reference's result
+ * depends on torch.topk's unspecified tie order among suppressed cells).
+ * ------------------------------------------------------------------------------------------------ */
+int b200romp_parse(const float* center_maps, const float* params_maps, int batch, int map_size, int n_betas,
+                   float thresh, int capacity, int* d_count, long long* batch_ids, long long* flat_inds,
+                   float* center_confs, float* params_pred, float* cam, float* thetas, float* betas,
+                   long long* center_preds, void* workspace, b200romp_stream stream);
+/* bytes of device scratch `workspace` must provide for `batch` frames */
+long long b200romp_parse_workspace_bytes(int batch);
+
+/* ------------------------------------------------------------------------------------------------
+ * Seam S3: `self.smpl_parser(outputs, root_align)` (main.py:168 -> smpl.py:62-108: lbs :111-188,
+ * batch_rodrigues :191-222, batch_rigid_transform :236-290, VertexJointSelector :24-35).
+ * Constant arrays are host fp32 / int64 with the packed-SMPL schema of pack_smpl_info.py:70-111.
+ * ------------------------------------------------------------------------------------------------ */
+b200romp_smpl* b200romp_smpl_create(int device, int n_betas, const float* v_template /*[6890,3]*/,
+                                    const float* shapedirs /*[6890,3,n_betas]*/, const float* posedirs /*[207,20670]*/,
+                                    const float* J_regressor /*[24,6890]*/, const float* weights /*[6890,24]*/,
+                                    const long long* parents /*[24]*/, const long long* extra_joints_index /*[21]*/,
+                                    const float* J_regressor_extra9 /*[9,6890]*/, const float* J_regressor_h36m17 /*[17,6890]*/);
+void b200romp_smpl_destroy(b200romp_smpl* smpl);
+/* floats of caller-provided device workspace needed per person */
+int b200romp_smpl_workspace_floats(void);
+/* betas [n,betas_stride>=n_betas] (first n_betas used), thetas [n,72] -> verts [n,6890,3], joints [n,71,3].
+ * If d_count != NULL the number of persons is min(n, *d_count) read on the device (no host sync). */
+int b200romp_smpl_forward(b200romp_smpl* smpl, const float* betas, int betas_stride, const float* thetas, int n,
+                          const int* d_count, int root_align, float* workspace, float* verts, float* joints,
+                          b200romp_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Seam S4: `body_mesh_projection2image(joints, cam, verts, offsets)` (post_parser.py:104-114;
+ * batch_orth_proj utils.py:309-315; convert_proejection_from_input_to_orgimg post_parser.py:81-88) and
+ * `convert_cam_to_3d_trans` (utils.py:303-307).  cam_trans_lsq is the closed-form least squares of
+ * utils.py:347-389 (the reference's own fallback for cv2.solvePnPRansac, utils.py:429-434), focal
+ * 443.4, image 512 (post_parser.py:99-100), solved in fp64 per person.
+ * offsets6 = host [top,bottom,left,right,h,w].  Optional outputs may be NULL.
+ * ------------------------------------------------------------------------------------------------ */
+int b200romp_project(const float* joints /*[n,71,3]*/, const float* verts /*[n,6890,3] or NULL*/, const float* cam /*[n,3]*/,
+                     int n, const int* d_count, const float* offsets6, float* pj2d_org /*[n,71,2]*/,
+                     float* verts_camed_org /*[n,6890,3] or NULL*/, float* cam_trans_weak /*[n,3] or NULL*/,
+                     float* cam_trans_lsq /*[n,3] or NULL*/, b200romp_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ROMP_H_ */

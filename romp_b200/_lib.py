@@ -1,0 +1,119 @@
+"""ctypes binding of libb200romp.so (C ABI declared in include/b200romp.h).
+
+The library is the product: if it is missing or fails to load this module raises - there is no
+PyTorch/CPU fallback path anywhere in ``romp_b200``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+LIB_PATH = os.path.join(HERE, "lib", "libb200romp.so")
+CSRC = os.path.join(HERE, "csrc")
+SOURCES = ["net.cu", "conv_simt.cu", "conv_tc.cu", "parse.cu", "smpl.cu", "project.cu"]
+
+F32, BF16, U8 = 0, 1, 2
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "in_", "in_c_off", "out", "out_c_off", "res", "res_c_off", "res_broadcast", "cin", "cout",
+        "ksize", "stride", "relu", "upsample", "input_norm", "pow_channel", "engine")]
+
+
+def nvcc_command(out_path=LIB_PATH):
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    return [nvcc, "-shared", "-Xcompiler", "-fPIC", "-std=c++17", "-O3", "-lineinfo",
+            "-gencode", "arch=compute_100a,code=sm_100a",
+            "-o", out_path] + [os.path.join(CSRC, s) for s in SOURCES]
+
+
+def needs_build():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "b200romp.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=True):
+    """Compile every CUDA source for sm_100a into romp_b200/lib/libb200romp.so (in-tree)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
+    cmd = nvcc_command()
+    if verbose:
+        print("[romp_b200] " + " ".join(cmd), file=sys.stderr)
+    subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def _sig(fn, restype, *argtypes):
+    fn.restype = restype
+    fn.argtypes = list(argtypes)
+
+
+def load():
+    """dlopen the library and declare every prototype of include/b200romp.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(romp_b200 has no fallback path without its CUDA library)")
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    vp, i32, f32, i64 = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+    fp, ip, lp = C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_longlong)
+    _sig(lib.b200romp_version, i32)
+    _sig(lib.b200romp_last_error, C.c_char_p)
+    _sig(lib.b200romp_device_info, i32, ip, ip, ip)
+    _sig(lib.b200romp_net_create, vp, i32)
+    _sig(lib.b200romp_net_destroy, None, vp)
+    _sig(lib.b200romp_net_add_tensor, i32, vp, i32, i32, i32, i32, i32, i32)
+    _sig(lib.b200romp_net_add_const_tensor, i32, vp, i32, i32, i32, i32, vp)
+    _sig(lib.b200romp_net_add_conv, i32, vp, C.POINTER(ConvDesc), fp, fp)
+    _sig(lib.b200romp_net_finalize, i32, vp, i32)
+    _sig(lib.b200romp_net_bind, i32, vp, i32, vp)
+    _sig(lib.b200romp_net_run, i32, vp, i32, vp)
+    _sig(lib.b200romp_net_read_tensor, i32, vp, i32, i32, vp, vp)
+    _sig(lib.b200romp_net_describe, i32, vp, C.c_char_p, i32)
+    _sig(lib.b200romp_net_num_launches, i32, vp)
+    _sig(lib.b200romp_net_workspace_bytes, i64, vp)
+    _sig(lib.b200romp_conv2d, i32, C.POINTER(ConvDesc), fp, fp, vp, i32, i32, i32, i32, vp, i32, i32, i32, vp, i32, i32, vp)
+    _sig(lib.b200romp_parse, i32, vp, vp, i32, i32, i32, f32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp)
+    _sig(lib.b200romp_parse_workspace_bytes, i64, i32)
+    _sig(lib.b200romp_smpl_create, vp, i32, i32, fp, fp, fp, fp, fp, lp, lp, fp, fp)
+    _sig(lib.b200romp_smpl_destroy, None, vp)
+    _sig(lib.b200romp_smpl_workspace_floats, i32)
+    _sig(lib.b200romp_smpl_forward, i32, vp, vp, i32, vp, i32, vp, i32, vp, vp, vp, vp)
+    _sig(lib.b200romp_project, i32, vp, vp, vp, i32, vp, fp, vp, vp, vp, vp, vp)
+    if lib.b200romp_version() != 100:
+        raise RuntimeError("libb200romp.so version mismatch - rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc is None or (isinstance(rc, int) and rc < 0):
+        msg = load().b200romp_last_error().decode()
+        raise RuntimeError(f"libb200romp {what} failed ({rc}): {msg}")
+    return rc
+
+
+EXPORTS = [
+    "b200romp_version", "b200romp_last_error", "b200romp_device_info", "b200romp_net_create",
+    "b200romp_net_destroy", "b200romp_net_add_tensor", "b200romp_net_add_const_tensor", "b200romp_net_add_conv",
+    "b200romp_net_finalize", "b200romp_net_bind", "b200romp_net_run", "b200romp_net_read_tensor",
+    "b200romp_net_describe", "b200romp_net_num_launches", "b200romp_net_workspace_bytes", "b200romp_conv2d",
+    "b200romp_parse", "b200romp_parse_workspace_bytes", "b200romp_smpl_create", "b200romp_smpl_destroy",
+    "b200romp_smpl_workspace_floats", "b200romp_smpl_forward", "b200romp_project",
+]

@@ -1,0 +1,27 @@
+// tcgen05 implicit-GEMM convolution engine (interface).  Implementation: conv_tc.cu
+#pragma once
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b200romp {
+
+struct TcConvPlan {
+  int kind = 0;                 // kernel family, 0 = none
+  int cin = 0, cout = 0, nt = 0;  // channels, output channels per CTA
+  int grid_x = 0, grid_y = 0;
+  int smem_bytes = 0;
+  void* d_wpack = nullptr;      // weights pre-arranged as the shared-memory image (bf16, swizzled)
+  alignas(64) unsigned char tmap_in[128];   // CUtensorMap for the NHWC input tensor
+  std::string describe() const;
+};
+
+// true when (shape, dtypes, flags) can run on the tcgen05 engine
+bool tc_conv_supported(const ConvParams& p, int ksize, int stride);
+// packs weights, builds tensor maps, picks the tiling; device allocations are appended to `allocs`
+int tc_conv_prepare(const ConvParams& p, int ksize, int stride, const float* w_oihw, int sm_count, TcConvPlan* plan,
+                    std::vector<void*>* allocs);
+int tc_conv_launch(const TcConvPlan& plan, const ConvParams& p, cudaStream_t stream);
+
+}  // namespace b200romp

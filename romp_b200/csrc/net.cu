@@ -1,0 +1,452 @@
+// Conv-graph runtime behind seam S1 (`self.model(image)`, simple_romp/romp/main.py:112).
+//
+// The host layer (romp_b200/graph.py) walks the reference's state-dict layout
+// (HigherResolutionNet model.py:246-417, ROMPv1 head :420-481), folds BatchNorm and emits one fused
+// conv op per Conv2d.  This file owns: tensor table, liveness-based buffer planning for the NHWC
+// activation workspace, weight packing/upload per engine, launch sequencing and CUDA-graph replay.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "conv_tc.cuh"
+
+namespace b200romp {
+
+static thread_local std::string g_last_error;
+
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+}
+
+struct Tensor {
+  int H, W, C, dtype, nchw, external;
+  void* ptr = nullptr;        // device pointer (workspace slice or bound external / constant)
+  bool constant = false;
+  int first_def = -1, last_use = -1;
+  size_t frame_bytes() const { return (size_t)H * W * C * dtype_size(dtype); }
+};
+
+struct Op {
+  b200romp_conv_desc d;
+  std::vector<float> w_host, b_host;   // OIHW fp32, [cout]
+  float* d_w_simt = nullptr;           // [tap][cin][coutPad]
+  float* d_bias = nullptr;             // [coutPad]
+  int coutPad = 0;
+  int engine = B200ROMP_ENGINE_SIMT;   // resolved
+  TcConvPlan tc;                       // tcgen05 plan (packed weights, tensor maps)
+};
+
+}  // namespace b200romp
+
+using namespace b200romp;
+
+struct b200romp_net {
+  int device = 0;
+  int sm_count = 148;
+  bool finalized = false;
+  int max_batch = 0;
+  std::vector<Tensor> tensors;
+  std::vector<Op> ops;
+  std::vector<void*> device_allocs;
+  char* workspace = nullptr;
+  size_t workspace_bytes = 0;
+  struct GraphKey {
+    int batch;
+    std::vector<void*> ext;
+    bool operator<(const GraphKey& o) const { return batch != o.batch ? batch < o.batch : ext < o.ext; }
+  };
+  std::map<GraphKey, cudaGraphExec_t> graphs;
+  bool use_graph = true;
+};
+
+static int fill_params(b200romp_net* net, const Op& op, int batch, ConvParams* out) {
+  const b200romp_conv_desc& d = op.d;
+  const Tensor& ti = net->tensors[d.in];
+  const Tensor& to = net->tensors[d.out];
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.in = ti.ptr; p.out = to.ptr;
+  p.w = op.d_w_simt; p.bias = op.d_bias;
+  p.B = batch;
+  p.Hin = ti.H; p.Win = ti.W; p.in_C = ti.C; p.in_c_off = d.in_c_off; p.cin = d.cin;
+  const int pad = d.ksize / 2;
+  p.Hout = (ti.H + 2 * pad - d.ksize) / d.stride + 1;
+  p.Wout = (ti.W + 2 * pad - d.ksize) / d.stride + 1;
+  p.out_C = to.C; p.out_c_off = d.out_c_off; p.cout = d.cout; p.coutPad = op.coutPad;
+  p.up = d.upsample;
+  if (d.res >= 0) {
+    const Tensor& tr = net->tensors[d.res];
+    p.res = tr.ptr; p.res_C = tr.C; p.res_c_off = op.d.res_c_off; p.res_broadcast = d.res_broadcast;
+    p.res_dtype = tr.dtype;
+  }
+  p.relu = d.relu; p.pow_channel = d.pow_channel; p.out_nchw = to.nchw;
+  p.in_dtype = ti.dtype; p.out_dtype = to.dtype; p.input_norm = d.input_norm;
+  if (!p.in || !p.out) {
+    set_error("op uses an unbound tensor (in=%d out=%d)", d.in, d.out);
+    return B200ROMP_ESTATE;
+  }
+  *out = p;
+  return B200ROMP_OK;
+}
+
+static int validate_desc(const std::vector<Tensor>& T, const b200romp_conv_desc& d) {
+  const int res_c_off = d.res_c_off;
+  auto ok_id = [&](int id) { return id >= 0 && id < (int)T.size(); };
+  B2R_REQUIRE(ok_id(d.in) && ok_id(d.out) && (d.res == -1 || ok_id(d.res)), "conv: bad tensor id");
+  B2R_REQUIRE((d.ksize == 1 || d.ksize == 3) && (d.stride == 1 || d.stride == 2), "conv: ksize/stride unsupported");
+  B2R_REQUIRE(d.upsample == 1 || d.upsample == 2 || d.upsample == 4 || d.upsample == 8, "conv: upsample must be 1,2,4,8");
+  const Tensor& ti = T[d.in];
+  const Tensor& to = T[d.out];
+  B2R_REQUIRE(!ti.nchw, "conv: NCHW inputs unsupported");
+  B2R_REQUIRE(d.cin > 0 && d.in_c_off >= 0 && d.in_c_off + d.cin <= ti.C, "conv: input channel slice out of range");
+  B2R_REQUIRE(d.cout > 0 && d.out_c_off >= 0 && d.out_c_off + d.cout <= to.C, "conv: output channel slice out of range");
+  const int pad = d.ksize / 2;
+  const int Ho = (ti.H + 2 * pad - d.ksize) / d.stride + 1, Wo = (ti.W + 2 * pad - d.ksize) / d.stride + 1;
+  B2R_REQUIRE(Ho * d.upsample == to.H && Wo * d.upsample == to.W, "conv: output tensor is %dx%d, op produces %dx%d",
+              to.H, to.W, Ho * d.upsample, Wo * d.upsample);
+  B2R_REQUIRE(ti.dtype != B200ROMP_U8 || d.input_norm, "conv: u8 input requires input_norm");
+  B2R_REQUIRE(to.dtype != B200ROMP_U8, "conv: u8 output unsupported");
+  B2R_REQUIRE(!to.nchw || to.dtype == B200ROMP_F32, "conv: NCHW output must be fp32");
+  if (d.res >= 0) {
+    const Tensor& tr = T[d.res];
+    B2R_REQUIRE(tr.H == to.H && tr.W == to.W && !tr.nchw && tr.dtype != B200ROMP_U8, "conv: residual shape/dtype mismatch");
+    B2R_REQUIRE(res_c_off >= 0 && res_c_off + d.cout <= tr.C, "conv: residual channel slice out of range");
+  }
+  return B200ROMP_OK;
+}
+
+extern "C" {
+
+int b200romp_version(void) { return B200ROMP_VERSION; }
+const char* b200romp_last_error(void) { return g_last_error.c_str(); }
+
+int b200romp_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  B2R_CUDA_OK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  B2R_CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  return B200ROMP_OK;
+}
+
+b200romp_net* b200romp_net_create(int device) {
+  if (cudaSetDevice(device) != cudaSuccess) {
+    set_error("cudaSetDevice(%d) failed - libb200romp needs a CUDA device (no CPU fallback)", device);
+    return nullptr;
+  }
+  b200romp_net* net = new b200romp_net();
+  net->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) net->sm_count = prop.multiProcessorCount;
+  const char* ng = getenv("B200ROMP_NO_GRAPH");
+  net->use_graph = !(ng && ng[0] == '1');
+  return net;
+}
+
+void b200romp_net_destroy(b200romp_net* net) {
+  if (!net) return;
+  cudaSetDevice(net->device);
+  for (auto& kv : net->graphs) cudaGraphExecDestroy(kv.second);
+  for (void* p : net->device_allocs) cudaFree(p);
+  if (net->workspace) cudaFree(net->workspace);
+  delete net;
+}
+
+int b200romp_net_add_tensor(b200romp_net* net, int H, int W, int C, int dtype, int nchw, int external) {
+  B2R_REQUIRE(net && !net->finalized, "add_tensor: net is null or finalized");
+  B2R_REQUIRE(H > 0 && W > 0 && C > 0 && dtype >= 0 && dtype <= 2, "add_tensor: bad shape/dtype");
+  Tensor t;
+  t.H = H; t.W = W; t.C = C; t.dtype = dtype; t.nchw = nchw; t.external = external;
+  net->tensors.push_back(t);
+  return (int)net->tensors.size() - 1;
+}
+
+// Constant tensor without a batch dimension (e.g. the coord-conv bias map of the ROMP head).
+int b200romp_net_add_const_tensor(b200romp_net* net, int H, int W, int C, int dtype, const void* host_data) {
+  int id = b200romp_net_add_tensor(net, H, W, C, dtype, 0, 0);
+  if (id < 0) return id;
+  Tensor& t = net->tensors[id];
+  t.constant = true;
+  B2R_CUDA_OK(cudaSetDevice(net->device));
+  B2R_CUDA_OK(cudaMalloc(&t.ptr, t.frame_bytes()));
+  net->device_allocs.push_back(t.ptr);
+  B2R_CUDA_OK(cudaMemcpy(t.ptr, host_data, t.frame_bytes(), cudaMemcpyHostToDevice));
+  return id;
+}
+
+int b200romp_net_add_conv(b200romp_net* net, const b200romp_conv_desc* desc, const float* weight, const float* bias) {
+  B2R_REQUIRE(net && !net->finalized && desc && weight, "add_conv: bad arguments");
+  int rc = validate_desc(net->tensors, *desc);
+  if (rc) return rc;
+  Op op;
+  op.d = *desc;
+  const size_t nw = (size_t)desc->cout * desc->cin * desc->ksize * desc->ksize;
+  op.w_host.assign(weight, weight + nw);
+  op.b_host.assign(desc->cout, 0.f);
+  if (bias) op.b_host.assign(bias, bias + desc->cout);
+  net->ops.push_back(std::move(op));
+  return (int)net->ops.size() - 1;
+}
+
+static int upload_simt_weights(b200romp_net* net, Op& op) {
+  const b200romp_conv_desc& d = op.d;
+  const int taps = d.ksize * d.ksize;
+  op.coutPad = (d.cout + 63) / 64 * 64;
+  std::vector<float> packed((size_t)taps * d.cin * op.coutPad, 0.f);
+  for (int co = 0; co < d.cout; ++co)
+    for (int ci = 0; ci < d.cin; ++ci)
+      for (int t = 0; t < taps; ++t)
+        packed[((size_t)t * d.cin + ci) * op.coutPad + co] = op.w_host[((size_t)co * d.cin + ci) * taps + t];
+  std::vector<float> bias(op.coutPad, 0.f);
+  std::copy(op.b_host.begin(), op.b_host.end(), bias.begin());
+  B2R_CUDA_OK(cudaMalloc(&op.d_w_simt, packed.size() * sizeof(float)));
+  net->device_allocs.push_back(op.d_w_simt);
+  B2R_CUDA_OK(cudaMemcpy(op.d_w_simt, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
+  B2R_CUDA_OK(cudaMalloc(&op.d_bias, bias.size() * sizeof(float)));
+  net->device_allocs.push_back(op.d_bias);
+  B2R_CUDA_OK(cudaMemcpy(op.d_bias, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return B200ROMP_OK;
+}
+
+int b200romp_net_finalize(b200romp_net* net, int max_batch) {
+  B2R_REQUIRE(net && !net->finalized && max_batch > 0, "finalize: bad arguments");
+  B2R_CUDA_OK(cudaSetDevice(net->device));
+  const int nT = (int)net->tensors.size(), nO = (int)net->ops.size();
+  // ---- liveness over the linear op order
+  for (int i = 0; i < nO; ++i) {
+    const b200romp_conv_desc& d = net->ops[i].d;
+    Tensor& to = net->tensors[d.out];
+    if (to.first_def < 0) to.first_def = i;
+    to.last_use = std::max(to.last_use, i);
+    net->tensors[d.in].last_use = std::max(net->tensors[d.in].last_use, i);
+    if (d.res >= 0) net->tensors[d.res].last_use = std::max(net->tensors[d.res].last_use, i);
+  }
+  for (int i = 0; i < nO; ++i) {
+    const b200romp_conv_desc& d = net->ops[i].d;
+    const Tensor& ti = net->tensors[d.in];
+    B2R_REQUIRE(ti.external || ti.constant || (ti.first_def >= 0 && ti.first_def < i), "op %d reads tensor %d before it is written", i, d.in);
+    if (d.res >= 0) {
+      const Tensor& tr = net->tensors[d.res];
+      B2R_REQUIRE(tr.external || tr.constant || (tr.first_def >= 0 && tr.first_def < i), "op %d adds tensor %d before it is written", i, d.res);
+    }
+  }
+  // ---- buffer planning: exact-size free lists, a buffer is recycled after its tensor's last use
+  struct Buf { size_t bytes; size_t offset; };
+  std::vector<Buf> bufs;
+  std::multimap<size_t, int> free_bufs;
+  std::vector<int> tensor_buf(nT, -1);
+  std::vector<std::vector<int>> dies_at(nO);
+  for (int t = 0; t < nT; ++t) {
+    const Tensor& tt = net->tensors[t];
+    if (!tt.external && !tt.constant && tt.first_def >= 0) dies_at[tt.last_use].push_back(t);
+  }
+  size_t total = 0;
+  for (int i = 0; i < nO; ++i) {
+    const int t = net->ops[i].d.out;
+    const Tensor& tt = net->tensors[t];
+    if (!tt.external && !tt.constant && tt.first_def == i) {
+      const size_t bytes = (tt.frame_bytes() * max_batch + 1023) / 1024 * 1024;
+      auto it = free_bufs.find(bytes);
+      if (it != free_bufs.end()) {
+        tensor_buf[t] = it->second;
+        free_bufs.erase(it);
+      } else {
+        bufs.push_back({bytes, total});
+        total += bytes;
+        tensor_buf[t] = (int)bufs.size() - 1;
+      }
+    }
+    for (int dead : dies_at[i]) free_bufs.insert({bufs[tensor_buf[dead]].bytes, tensor_buf[dead]});
+  }
+  if (total > 0) {
+    B2R_CUDA_OK(cudaMalloc(&net->workspace, total));
+    B2R_CUDA_OK(cudaMemset(net->workspace, 0, total));
+  }
+  net->workspace_bytes = total;
+  for (int t = 0; t < nT; ++t)
+    if (tensor_buf[t] >= 0) net->tensors[t].ptr = net->workspace + bufs[tensor_buf[t]].offset;
+  net->max_batch = max_batch;
+  // ---- engine resolution + weight upload
+  for (int i = 0; i < nO; ++i) {
+    Op& op = net->ops[i];
+    int rc = upload_simt_weights(net, op);
+    if (rc) return rc;
+    op.engine = B200ROMP_ENGINE_SIMT;
+    const Tensor& ti = net->tensors[op.d.in];
+    const Tensor& to = net->tensors[op.d.out];
+    const bool want_tc = op.d.engine == B200ROMP_ENGINE_TCGEN05 ||
+                         (op.d.engine == B200ROMP_ENGINE_AUTO && ti.dtype == B200ROMP_BF16);
+    if (want_tc) {
+      ConvParams p;
+      // tensor pointers of internal tensors are final now; external ones are re-bound per run and are
+      // never routed to the tcgen05 engine (stem input / NCHW map outputs stay on the SIMT engine).
+      if (!ti.external && !to.external && fill_params(net, op, max_batch, &p) == B200ROMP_OK &&
+          tc_conv_supported(p, op.d.ksize, op.d.stride)) {
+        rc = tc_conv_prepare(p, op.d.ksize, op.d.stride, op.w_host.data(), net->sm_count, &op.tc, &net->device_allocs);
+        if (rc == B200ROMP_OK) op.engine = B200ROMP_ENGINE_TCGEN05;
+        else if (op.d.engine == B200ROMP_ENGINE_TCGEN05) return rc;
+      } else if (op.d.engine == B200ROMP_ENGINE_TCGEN05) {
+        set_error("op %d: tcgen05 engine forced but shape unsupported", i);
+        return B200ROMP_EINVAL;
+      }
+    }
+    op.w_host.clear(); op.w_host.shrink_to_fit();
+  }
+  net->finalized = true;
+  return B200ROMP_OK;
+}
+
+int b200romp_net_bind(b200romp_net* net, int tensor, void* device_ptr) {
+  B2R_REQUIRE(net && tensor >= 0 && tensor < (int)net->tensors.size(), "bind: bad tensor id");
+  B2R_REQUIRE(net->tensors[tensor].external, "bind: tensor %d is not external", tensor);
+  net->tensors[tensor].ptr = device_ptr;
+  return B200ROMP_OK;
+}
+
+static int enqueue_all(b200romp_net* net, int batch, cudaStream_t stream) {
+  for (size_t i = 0; i < net->ops.size(); ++i) {
+    Op& op = net->ops[i];
+    ConvParams p;
+    int rc = fill_params(net, op, batch, &p);
+    if (rc) return rc;
+    if (op.engine == B200ROMP_ENGINE_TCGEN05) rc = tc_conv_launch(op.tc, p, stream);
+    else rc = launch_conv_simt(p, op.d.ksize, op.d.stride, stream);
+    if (rc) return rc;
+  }
+  return B200ROMP_OK;
+}
+
+int b200romp_net_run(b200romp_net* net, int batch, b200romp_stream stream_) {
+  B2R_REQUIRE(net && net->finalized, "run: net not finalized");
+  B2R_REQUIRE(batch > 0 && batch <= net->max_batch, "run: batch %d outside 1..%d", batch, net->max_batch);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B2R_CUDA_OK(cudaSetDevice(net->device));
+  if (!net->use_graph || stream == nullptr) return enqueue_all(net, batch, stream);
+  b200romp_net::GraphKey key;
+  key.batch = batch;
+  for (const Tensor& t : net->tensors)
+    if (t.external) key.ext.push_back(t.ptr);
+  auto it = net->graphs.find(key);
+  if (it == net->graphs.end()) {
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return enqueue_all(net, batch, stream);   // stream cannot capture (e.g. legacy default stream)
+    }
+    int rc = enqueue_all(net, batch, stream);
+    e = cudaStreamEndCapture(stream, &graph);
+    if (rc) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    B2R_CUDA_OK(e);
+    cudaGraphExec_t exec = nullptr;
+    B2R_CUDA_OK(cudaGraphInstantiate(&exec, graph, 0));
+    cudaGraphDestroy(graph);
+    if (net->graphs.size() > 16) {   // bound the cache: callers normally cycle through a few buffers
+      for (auto& kv : net->graphs) cudaGraphExecDestroy(kv.second);
+      net->graphs.clear();
+    }
+    it = net->graphs.insert({key, exec}).first;
+  }
+  B2R_CUDA_OK(cudaGraphLaunch(it->second, stream));
+  return B200ROMP_OK;
+}
+
+int b200romp_net_read_tensor(b200romp_net* net, int tensor, int batch, void* dst, b200romp_stream stream) {
+  B2R_REQUIRE(net && net->finalized && tensor >= 0 && tensor < (int)net->tensors.size(), "read_tensor: bad arguments");
+  const Tensor& t = net->tensors[tensor];
+  B2R_REQUIRE(t.ptr != nullptr, "read_tensor: tensor %d has no storage", tensor);
+  const size_t bytes = t.frame_bytes() * (t.constant ? 1 : batch);
+  B2R_CUDA_OK(cudaMemcpyAsync(dst, t.ptr, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return B200ROMP_OK;
+}
+
+int b200romp_net_describe(b200romp_net* net, char* buf, int len) {
+  if (!net || !buf || len <= 0) return B200ROMP_EINVAL;
+  std::string s;
+  char line[256];
+  for (size_t i = 0; i < net->ops.size(); ++i) {
+    const Op& op = net->ops[i];
+    const b200romp_conv_desc& d = op.d;
+    const Tensor& ti = net->tensors[d.in];
+    const Tensor& to = net->tensors[d.out];
+    snprintf(line, sizeof(line), "op%03zu %s k%d s%d %4d->%-4d in t%d[%dx%dx%d]+%d out t%d[%dx%dx%d]+%d res t%d up%d relu%d%s\n", i,
+             op.engine == B200ROMP_ENGINE_TCGEN05 ? "tcgen05" : "simt   ", d.ksize, d.stride, d.cin, d.cout, d.in, ti.H,
+             ti.W, ti.C, d.in_c_off, d.out, to.H, to.W, to.C, d.out_c_off, d.res, d.upsample, d.relu,
+             op.engine == B200ROMP_ENGINE_TCGEN05 ? op.tc.describe().c_str() : "");
+    s += line;
+  }
+  snprintf(line, sizeof(line), "workspace %.1f MiB for max_batch %d\n", net->workspace_bytes / 1048576.0, net->max_batch);
+  s += line;
+  const int n = (int)std::min<size_t>(s.size(), (size_t)len - 1);
+  memcpy(buf, s.data(), n);
+  buf[n] = 0;
+  return n;
+}
+
+int b200romp_net_num_launches(b200romp_net* net) { return net ? (int)net->ops.size() : 0; }
+long long b200romp_net_workspace_bytes(b200romp_net* net) { return net ? (long long)net->workspace_bytes : 0; }
+
+int b200romp_conv2d(const b200romp_conv_desc* d, const float* weight_host, const float* bias_host, const void* in,
+                    int in_dtype, int in_H, int in_W, int in_C, void* out, int out_dtype, int out_C, int out_nchw,
+                    const void* res, int res_dtype, int batch, b200romp_stream stream) {
+  B2R_REQUIRE(d && weight_host && in && out && batch > 0, "conv2d: bad arguments");
+  int dev = 0;
+  B2R_CUDA_OK(cudaGetDevice(&dev));
+  b200romp_net* net = b200romp_net_create(dev);
+  if (!net) return B200ROMP_ECUDA;
+  const int pad = d->ksize / 2;
+  const int Ho = ((in_H + 2 * pad - d->ksize) / d->stride + 1) * d->upsample;
+  const int Wo = ((in_W + 2 * pad - d->ksize) / d->stride + 1) * d->upsample;
+  b200romp_conv_desc dd = *d;
+  dd.in = b200romp_net_add_tensor(net, in_H, in_W, in_C, in_dtype, 0, 1);
+  dd.out = b200romp_net_add_tensor(net, Ho, Wo, out_C, out_dtype, out_nchw, 1);
+  dd.res = -1;
+  if (res) dd.res = b200romp_net_add_tensor(net, Ho, Wo, out_C, res_dtype, 0, 1);
+  int rc = (dd.in < 0 || dd.out < 0) ? B200ROMP_EINVAL : B200ROMP_OK;
+  if (!rc) {
+    net->tensors[dd.in].ptr = const_cast<void*>(in);
+    net->tensors[dd.out].ptr = out;
+    if (res) net->tensors[dd.res].ptr = const_cast<void*>(res);
+    // stand-alone call: external tensors are allowed on the tcgen05 engine because pointers are final
+    net->tensors[dd.in].external = net->tensors[dd.out].external = 0;
+    if (res) net->tensors[dd.res].external = 0;
+    net->tensors[dd.in].constant = true;   // skip "written before read" checks and workspace planning
+    net->tensors[dd.out].constant = true;
+    if (res) net->tensors[dd.res].constant = true;
+    dd.res_c_off = d->out_c_off;
+    rc = b200romp_net_add_conv(net, &dd, weight_host, bias_host);
+    rc = rc < 0 ? rc : B200ROMP_OK;
+  }
+  if (!rc) rc = b200romp_net_finalize(net, batch);
+  if (!rc) {
+    net->use_graph = false;
+    rc = b200romp_net_run(net, batch, stream);
+  }
+  if (!rc) {
+    cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);   // weights are freed below
+    if (e != cudaSuccess) {
+      set_error("conv2d: %s", cudaGetErrorString(e));
+      rc = B200ROMP_ECUDA;
+    }
+  }
+  b200romp_net_destroy(net);
+  return rc;
+}
+
+}  // extern "C"

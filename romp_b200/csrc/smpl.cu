@@ -1,0 +1,401 @@
+// Seam S3: SMPL forward (fp32), fused so that vertices are written to HBM exactly once.
+//
+// Replaces simple_romp/romp/smpl.py: SMPL.forward :62-108, lbs :111-188, batch_rodrigues :191-222,
+// transform_mat :224-234, batch_rigid_transform :236-290, VertexJointSelector.forward :24-35.
+// The reference materialises v_shaped, pose_offsets, T[N,6890,4,4] (441 KB/person written and re-read)
+// and runs the kinematic chain as 23 serial launches; here:
+//
+//   K1 smpl_pose_kernel   (1 warp / person): Rodrigues, joint regression, kinematic chain by tree level,
+//        relative transforms A[24][3x4], pose feature; writes 24 posed joints.   ~2 KB/person scratch.
+//   K2 smpl_verts_kernel  (CTA = 128 vertices x 32 persons): v_posed = v_t + [betas|pose_feature] x
+//        [shapedirs;posedirs] (one K=10+207 contraction), T = W x A, vert = T [v_posed;1]; verts written once.
+//        Algorithmic HBM bytes/person: 328 B in + 82,680 B verts + 852 B joints.
+//   K3 smpl_joints_kernel (CTA / person): 21 picked vertices + 9 + 17 regressed joints from CSR rows of
+//        the (sparse in real SMPL, any density accepted) regressors; optional root alignment.
+//   K4 smpl_root_align_kernel: verts -= root (only when root_align, smpl.py:102-106).
+//
+// J = J_regressor x (v_t + S b) is evaluated as (J_regressor v_t) + (J_regressor S) b with the two
+// products precomputed in fp64 at create time (linear identity; differences ~1e-7, tolerance 1e-4).
+#include <vector>
+
+#include "common.cuh"
+
+namespace b200romp {
+
+constexpr int kV = 6890;
+constexpr int kJ = 24;
+constexpr int kWsFloats = 512;   // per-person scratch: [0,224) features, [224,512) A[24][12]
+constexpr int kFeatOff = 0, kAOff = 224;
+constexpr int kMaxBetas = 16;
+
+__constant__ int c_parents[kJ];
+__constant__ int c_depth[kJ];
+
+struct SmplDev {
+  int n_betas, K;               // K = n_betas + 207
+  const float* v_template;      // [6890*3]
+  const float* blend;           // [K][20670]  rows: shapedirs^T then posedirs
+  const float* weights;         // [6890][24]
+  const float* J_template;      // [24*3]
+  const float* J_shape;         // [24*3][n_betas]
+  const int* extra_idx;         // [21]
+  const int* csr_rowptr;        // [27]
+  const int* csr_col;
+  const float* csr_val;
+};
+
+__device__ __forceinline__ int person_count(int n, const int* d_count) {
+  return d_count ? min(n, *d_count) : n;
+}
+
+__global__ void __launch_bounds__(128) smpl_pose_kernel(SmplDev m, const float* __restrict__ betas, int betas_stride,
+                                                        const float* __restrict__ thetas, int n_host,
+                                                        const int* __restrict__ d_count, float* __restrict__ ws,
+                                                        float* __restrict__ joints) {
+  __shared__ float s_J[4][kJ][3];
+  __shared__ float s_G[4][kJ][12];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 4 + warp;
+  const int N = person_count(n_host, d_count);
+  if (n >= N) return;    // whole warp exits together; only __syncwarp is used below
+  float* w = ws + (size_t)n * kWsFloats;
+  const float* be = betas + (size_t)n * betas_stride;
+  float R[9], Jl[3] = {0.f, 0.f, 0.f};
+  if (lane < m.n_betas) w[kFeatOff + lane] = be[lane];
+  if (lane < kJ) {
+    // batch_rodrigues, smpl.py:206-221
+    const float rx0 = thetas[(size_t)n * 72 + lane * 3 + 0];
+    const float ry0 = thetas[(size_t)n * 72 + lane * 3 + 1];
+    const float rz0 = thetas[(size_t)n * 72 + lane * 3 + 2];
+    const float ex = rx0 + 1e-8f, ey = ry0 + 1e-8f, ez = rz0 + 1e-8f;
+    const float angle = sqrtf(ex * ex + ey * ey + ez * ez);
+    const float rx = rx0 / angle, ry = ry0 / angle, rz = rz0 / angle;
+    const float s = sinf(angle), c1 = 1.f - cosf(angle);
+    const float K[9] = {0.f, -rz, ry, rz, 0.f, -rx, -ry, rx, 0.f};
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        float kk = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) kk += K[a * 3 + c] * K[c * 3 + b];
+        R[a * 3 + b] = (a == b ? 1.f : 0.f) + s * K[a * 3 + b] + c1 * kk;
+      }
+    // J = J_regressor (v_template + shapedirs betas), smpl.py:153-156
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      float acc = m.J_template[lane * 3 + k];
+      for (int l = 0; l < m.n_betas; ++l) acc = fmaf(m.J_shape[(lane * 3 + k) * m.n_betas + l], be[l], acc);
+      Jl[k] = acc;
+      s_J[warp][lane][k] = acc;
+    }
+    if (lane >= 1) {   // pose_feature = (R[1:] - I).view(207), smpl.py:165
+#pragma unroll
+      for (int e = 0; e < 9; ++e) w[kFeatOff + m.n_betas + (lane - 1) * 9 + e] = R[e] - ((e % 4 == 0) ? 1.f : 0.f);
+    }
+  }
+  __syncwarp();
+  // kinematic chain by tree depth (batch_rigid_transform, smpl.py:260-277): G_i = G_parent * [R_i | J_i - J_parent]
+  float G[12];
+  for (int level = 0; level < 9; ++level) {
+    if (lane < kJ && c_depth[lane] == level) {
+      if (level == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          G[a * 4 + 0] = R[a * 3 + 0]; G[a * 4 + 1] = R[a * 3 + 1]; G[a * 4 + 2] = R[a * 3 + 2];
+          G[a * 4 + 3] = Jl[a];
+        }
+      } else {
+        const int p = c_parents[lane];
+        const float t0 = Jl[0] - s_J[warp][p][0], t1 = Jl[1] - s_J[warp][p][1], t2 = Jl[2] - s_J[warp][p][2];
+        float P[12];
+#pragma unroll
+        for (int e = 0; e < 12; ++e) P[e] = s_G[warp][p][e];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+#pragma unroll
+          for (int b = 0; b < 3; ++b)
+            G[a * 4 + b] = P[a * 4 + 0] * R[0 * 3 + b] + P[a * 4 + 1] * R[1 * 3 + b] + P[a * 4 + 2] * R[2 * 3 + b];
+          G[a * 4 + 3] = P[a * 4 + 0] * t0 + P[a * 4 + 1] * t1 + P[a * 4 + 2] * t2 + P[a * 4 + 3];
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 12; ++e) s_G[warp][lane][e] = G[e];
+    }
+    __syncwarp();
+  }
+  if (lane < kJ) {
+    // posed joints (:280) and A = G - [0 | G [J;0]] (:285-288)
+    float* jo = joints + ((size_t)n * 71 + lane) * 3;
+    jo[0] = G[3]; jo[1] = G[7]; jo[2] = G[11];
+    float* A = w + kAOff + lane * 12;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      A[a * 4 + 0] = G[a * 4 + 0]; A[a * 4 + 1] = G[a * 4 + 1]; A[a * 4 + 2] = G[a * 4 + 2];
+      A[a * 4 + 3] = G[a * 4 + 3] - (G[a * 4 + 0] * Jl[0] + G[a * 4 + 1] * Jl[1] + G[a * 4 + 2] * Jl[2]);
+    }
+  }
+}
+
+constexpr int kVT = 128;   // vertices per CTA
+constexpr int kPT = 32;    // persons per CTA (two halves of 16)
+
+__global__ void __launch_bounds__(256) smpl_verts_kernel(SmplDev m, int n_host, const int* __restrict__ d_count,
+                                                         const float* __restrict__ ws, float* __restrict__ verts) {
+  extern __shared__ __align__(16) float smem[];
+  float* s_feat = smem;                       // [K][32]
+  float* s_A = smem + 224 * kPT;              // [32][288]
+  const int N = person_count(n_host, d_count);
+  const int n0 = blockIdx.y * kPT;
+  if (n0 >= N) return;
+  const int tid = threadIdx.x;
+  const int K = m.K;
+  for (int i = tid; i < K * kPT; i += 256) {
+    const int q = i % kPT, p = i / kPT;
+    s_feat[p * kPT + q] = (n0 + q < N) ? ws[(size_t)(n0 + q) * kWsFloats + kFeatOff + p] : 0.f;
+  }
+  for (int i = tid; i < kPT * 288; i += 256) {
+    const int q = i / 288, e = i % 288;
+    s_A[i] = (n0 + q < N) ? ws[(size_t)(n0 + q) * kWsFloats + kAOff + e] : 0.f;
+  }
+  __syncthreads();
+  const int half = tid >> 7;
+  const int v = blockIdx.x * kVT + (tid & 127);
+  if (v >= kV) return;
+  float acc[16][3];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) acc[q][0] = acc[q][1] = acc[q][2] = 0.f;
+  const float* bl = m.blend + (size_t)3 * v;
+#pragma unroll 4
+  for (int p = 0; p < K; ++p) {
+    const float b0 = bl[(size_t)p * (3 * kV) + 0], b1 = bl[(size_t)p * (3 * kV) + 1], b2 = bl[(size_t)p * (3 * kV) + 2];
+    const float4* f4 = reinterpret_cast<const float4*>(s_feat + p * kPT + half * 16);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const float4 f = f4[g];
+      acc[g * 4 + 0][0] = fmaf(f.x, b0, acc[g * 4 + 0][0]); acc[g * 4 + 0][1] = fmaf(f.x, b1, acc[g * 4 + 0][1]); acc[g * 4 + 0][2] = fmaf(f.x, b2, acc[g * 4 + 0][2]);
+      acc[g * 4 + 1][0] = fmaf(f.y, b0, acc[g * 4 + 1][0]); acc[g * 4 + 1][1] = fmaf(f.y, b1, acc[g * 4 + 1][1]); acc[g * 4 + 1][2] = fmaf(f.y, b2, acc[g * 4 + 1][2]);
+      acc[g * 4 + 2][0] = fmaf(f.z, b0, acc[g * 4 + 2][0]); acc[g * 4 + 2][1] = fmaf(f.z, b1, acc[g * 4 + 2][1]); acc[g * 4 + 2][2] = fmaf(f.z, b2, acc[g * 4 + 2][2]);
+      acc[g * 4 + 3][0] = fmaf(f.w, b0, acc[g * 4 + 3][0]); acc[g * 4 + 3][1] = fmaf(f.w, b1, acc[g * 4 + 3][1]); acc[g * 4 + 3][2] = fmaf(f.w, b2, acc[g * 4 + 3][2]);
+    }
+  }
+  const float vt0 = m.v_template[3 * v + 0], vt1 = m.v_template[3 * v + 1], vt2 = m.v_template[3 * v + 2];
+  float wj[kJ];
+  {
+    const float4* w4 = reinterpret_cast<const float4*>(m.weights + (size_t)v * kJ);
+#pragma unroll
+    for (int g = 0; g < 6; ++g) {
+      const float4 t = w4[g];
+      wj[g * 4 + 0] = t.x; wj[g * 4 + 1] = t.y; wj[g * 4 + 2] = t.z; wj[g * 4 + 3] = t.w;
+    }
+  }
+#pragma unroll 2
+  for (int q = 0; q < 16; ++q) {
+    const int n = n0 + half * 16 + q;
+    if (n >= N) break;
+    const float4* A4 = reinterpret_cast<const float4*>(s_A + (half * 16 + q) * 288);
+    float4 T0 = make_float4(0.f, 0.f, 0.f, 0.f), T1 = T0, T2 = T0;
+#pragma unroll
+    for (int j = 0; j < kJ; ++j) {
+      const float4 a0 = A4[j * 3 + 0], a1 = A4[j * 3 + 1], a2 = A4[j * 3 + 2];
+      const float w = wj[j];
+      T0.x = fmaf(w, a0.x, T0.x); T0.y = fmaf(w, a0.y, T0.y); T0.z = fmaf(w, a0.z, T0.z); T0.w = fmaf(w, a0.w, T0.w);
+      T1.x = fmaf(w, a1.x, T1.x); T1.y = fmaf(w, a1.y, T1.y); T1.z = fmaf(w, a1.z, T1.z); T1.w = fmaf(w, a1.w, T1.w);
+      T2.x = fmaf(w, a2.x, T2.x); T2.y = fmaf(w, a2.y, T2.y); T2.z = fmaf(w, a2.z, T2.z); T2.w = fmaf(w, a2.w, T2.w);
+    }
+    const float px = vt0 + acc[q][0], py = vt1 + acc[q][1], pz = vt2 + acc[q][2];
+    float* o = verts + ((size_t)n * kV + v) * 3;
+    o[0] = T0.x * px + T0.y * py + T0.z * pz + T0.w;
+    o[1] = T1.x * px + T1.y * py + T1.z * pz + T1.w;
+    o[2] = T2.x * px + T2.y * py + T2.z * pz + T2.w;
+  }
+}
+
+__global__ void __launch_bounds__(256) smpl_joints_kernel(SmplDev m, int n_host, const int* __restrict__ d_count,
+                                                          const float* __restrict__ verts, int root_align,
+                                                          float* __restrict__ joints, float* __restrict__ ws) {
+  __shared__ float s_root[3];
+  const int n = blockIdx.x;
+  const int N = person_count(n_host, d_count);
+  if (n >= N) return;
+  const float* vp = verts + (size_t)n * kV * 3;
+  float* jo = joints + (size_t)n * 71 * 3;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < 21 * 3) {   // index_select of 21 vertices, smpl.py:25
+    const int j = tid / 3, k = tid % 3;
+    jo[(24 + j) * 3 + k] = vp[(size_t)m.extra_idx[j] * 3 + k];
+  }
+  for (int row = warp; row < 26; row += 8) {   // einsum('bik,ji->bjk') for the 9 + 17 regressors, smpl.py:26-27
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int e = m.csr_rowptr[row] + lane; e < m.csr_rowptr[row + 1]; e += 32) {
+      const float w = m.csr_val[e];
+      const float* q = vp + (size_t)m.csr_col[e] * 3;
+      a0 = fmaf(w, q[0], a0); a1 = fmaf(w, q[1], a1); a2 = fmaf(w, q[2], a2);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    if (lane == 0) {
+      jo[(45 + row) * 3 + 0] = a0; jo[(45 + row) * 3 + 1] = a1; jo[(45 + row) * 3 + 2] = a2;
+    }
+  }
+  if (!root_align) return;
+  __syncthreads();   // joints 45,46 written by warps 0,1 of this CTA (global writes visible after the barrier)
+  if (tid < 3) {
+    const float r = (jo[45 * 3 + tid] + jo[46 * 3 + tid]) / 2.f;   // joints54[:,[45,46]].mean(1), smpl.py:104
+    s_root[tid] = r;
+    ws[(size_t)n * kWsFloats + kFeatOff + tid] = r;               // feature slots are dead by now
+  }
+  __syncthreads();
+  for (int i = tid; i < 71 * 3; i += 256) jo[i] -= s_root[i % 3];
+}
+
+__global__ void __launch_bounds__(256) smpl_root_align_kernel(int n_host, const int* __restrict__ d_count,
+                                                              const float* __restrict__ ws, float* __restrict__ verts) {
+  const int n = blockIdx.x;
+  if (n >= person_count(n_host, d_count)) return;
+  const int i = blockIdx.y * 256 + threadIdx.x;
+  if (i >= kV * 3) return;
+  verts[(size_t)n * kV * 3 + i] -= ws[(size_t)n * kWsFloats + kFeatOff + (i % 3)];
+}
+
+}  // namespace b200romp
+
+using namespace b200romp;
+
+struct b200romp_smpl {
+  int device = 0;
+  SmplDev dev;
+  std::vector<void*> allocs;
+  int smem_verts = 0;
+};
+
+template <typename T>
+static int upload(b200romp_smpl* s, const std::vector<T>& host, const T** out) {
+  void* d = nullptr;
+  B2R_CUDA_OK(cudaMalloc(&d, host.size() * sizeof(T)));
+  s->allocs.push_back(d);
+  B2R_CUDA_OK(cudaMemcpy(d, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *out = reinterpret_cast<const T*>(d);
+  return B200ROMP_OK;
+}
+
+extern "C" {
+
+int b200romp_smpl_workspace_floats(void) { return kWsFloats; }
+
+b200romp_smpl* b200romp_smpl_create(int device, int n_betas, const float* v_template, const float* shapedirs,
+                                    const float* posedirs, const float* J_regressor, const float* weights,
+                                    const long long* parents, const long long* extra_joints_index,
+                                    const float* J_regressor_extra9, const float* J_regressor_h36m17) {
+  if (!v_template || !shapedirs || !posedirs || !J_regressor || !weights || !parents || !extra_joints_index ||
+      !J_regressor_extra9 || !J_regressor_h36m17 || n_betas < 1 || n_betas > kMaxBetas) {
+    set_error("smpl_create: bad arguments");
+    return nullptr;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) {
+    set_error("smpl_create: cudaSetDevice(%d) failed (no CPU fallback)", device);
+    return nullptr;
+  }
+  int par[kJ], depth[kJ];
+  for (int j = 0; j < kJ; ++j) {
+    par[j] = (int)parents[j];
+    if (j == 0) par[j] = -1;
+    if (j > 0 && (par[j] < 0 || par[j] >= j)) {
+      set_error("smpl_create: kintree_table must satisfy 0 <= parent[j] < j");
+      return nullptr;
+    }
+    depth[j] = j == 0 ? 0 : depth[par[j]] + 1;
+    if (depth[j] > 8) {
+      set_error("smpl_create: kinematic tree deeper than 9 levels");
+      return nullptr;
+    }
+  }
+  b200romp_smpl* s = new b200romp_smpl();
+  s->device = device;
+  const int K = n_betas + 207;
+  bool ok = cudaMemcpyToSymbol(c_parents, par, sizeof(par)) == cudaSuccess &&
+            cudaMemcpyToSymbol(c_depth, depth, sizeof(depth)) == cudaSuccess;
+  // blend matrix: rows 0..n_betas-1 = shapedirs[:, :, l] flattened, then posedirs
+  std::vector<float> blend((size_t)K * 3 * kV);
+  for (int l = 0; l < n_betas; ++l)
+    for (int i = 0; i < 3 * kV; ++i) blend[(size_t)l * 3 * kV + i] = shapedirs[(size_t)i * n_betas + l];
+  std::copy(posedirs, posedirs + (size_t)207 * 3 * kV, blend.begin() + (size_t)n_betas * 3 * kV);
+  std::vector<float> Jt(kJ * 3), Js((size_t)kJ * 3 * n_betas);
+  for (int j = 0; j < kJ; ++j)
+    for (int k = 0; k < 3; ++k) {
+      double a = 0.0;
+      for (int v = 0; v < kV; ++v) a += (double)J_regressor[(size_t)j * kV + v] * v_template[v * 3 + k];
+      Jt[j * 3 + k] = (float)a;
+      for (int l = 0; l < n_betas; ++l) {
+        double b = 0.0;
+        for (int v = 0; v < kV; ++v)
+          b += (double)J_regressor[(size_t)j * kV + v] * shapedirs[((size_t)v * 3 + k) * n_betas + l];
+        Js[((size_t)j * 3 + k) * n_betas + l] = (float)b;
+      }
+    }
+  std::vector<int> rowptr(27, 0), cols;
+  std::vector<float> vals;
+  for (int r = 0; r < 26; ++r) {
+    const float* row = r < 9 ? J_regressor_extra9 + (size_t)r * kV : J_regressor_h36m17 + (size_t)(r - 9) * kV;
+    for (int v = 0; v < kV; ++v)
+      if (row[v] != 0.f) {
+        cols.push_back(v);
+        vals.push_back(row[v]);
+      }
+    rowptr[r + 1] = (int)cols.size();
+  }
+  if (cols.empty()) { cols.push_back(0); vals.push_back(0.f); }
+  std::vector<int> eidx(21);
+  for (int i = 0; i < 21; ++i) {
+    eidx[i] = (int)extra_joints_index[i];
+    if (eidx[i] < 0 || eidx[i] >= kV) ok = false;
+  }
+  std::vector<float> vt(v_template, v_template + 3 * kV), w(weights, weights + (size_t)kV * kJ);
+  SmplDev& d = s->dev;
+  d.n_betas = n_betas; d.K = K;
+  ok = ok && upload(s, vt, &d.v_template) == 0 && upload(s, blend, &d.blend) == 0 && upload(s, w, &d.weights) == 0 &&
+       upload(s, Jt, &d.J_template) == 0 && upload(s, Js, &d.J_shape) == 0 && upload(s, eidx, &d.extra_idx) == 0 &&
+       upload(s, rowptr, &d.csr_rowptr) == 0 && upload(s, cols, &d.csr_col) == 0 && upload(s, vals, &d.csr_val) == 0;
+  s->smem_verts = (224 * kPT + kPT * 288) * (int)sizeof(float);
+  ok = ok && cudaFuncSetAttribute(smpl_verts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_verts) == cudaSuccess;
+  if (!ok) {
+    set_error("smpl_create: upload failed (%s)", cudaGetErrorString(cudaGetLastError()));
+    b200romp_smpl_destroy(s);
+    return nullptr;
+  }
+  return s;
+}
+
+void b200romp_smpl_destroy(b200romp_smpl* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  for (void* p : s->allocs) cudaFree(p);
+  delete s;
+}
+
+int b200romp_smpl_forward(b200romp_smpl* s, const float* betas, int betas_stride, const float* thetas, int n,
+                          const int* d_count, int root_align, float* workspace, float* verts, float* joints,
+                          b200romp_stream stream_) {
+  B2R_REQUIRE(s && betas && thetas && workspace && verts && joints, "smpl_forward: null pointer");
+  B2R_REQUIRE(n > 0 && betas_stride >= s->dev.n_betas, "smpl_forward: n must be > 0 and betas_stride >= n_betas");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  smpl_pose_kernel<<<(n + 3) / 4, 128, 0, stream>>>(s->dev, betas, betas_stride, thetas, n, d_count, workspace, joints);
+  B2R_CUDA_OK(cudaGetLastError());
+  dim3 grid((kV + kVT - 1) / kVT, (n + kPT - 1) / kPT);
+  smpl_verts_kernel<<<grid, 256, s->smem_verts, stream>>>(s->dev, n, d_count, workspace, verts);
+  B2R_CUDA_OK(cudaGetLastError());
+  smpl_joints_kernel<<<n, 256, 0, stream>>>(s->dev, n, d_count, verts, root_align, joints, workspace);
+  B2R_CUDA_OK(cudaGetLastError());
+  if (root_align) {
+    dim3 g2(n, (kV * 3 + 255) / 256);
+    smpl_root_align_kernel<<<g2, 256, 0, stream>>>(n, d_count, workspace, verts);
+    B2R_CUDA_OK(cudaGetLastError());
+  }
+  return B200ROMP_OK;
+}
+
+}  // extern "C"

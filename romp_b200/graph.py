@@ -1,0 +1,199 @@
+"""Host-side graph builder for seam S1: turns the reference's ROMPv1 state dict into the fused conv ops
+executed by libb200romp (b200romp_net_*).
+
+It mirrors the *structure* of simple_romp/romp/model.py (HigherResolutionNet :246-417, HighResolutionModule
+:129-244, Bottleneck :85-123, BasicBlock :54-83, ROMPv1 head :420-481) and consumes exactly the
+reference's state-dict keys, so a released ``ROMP.pkl`` loads unchanged.  Work done here is weight
+preprocessing only (BatchNorm folding, constant folding of the coord-map channels); every per-frame FLOP
+runs in the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from ._lib import BF16, F32, U8, ConvDesc
+
+BN_EPS = 1e-5
+
+
+def fold_bn(sd, conv, bn):
+    """Conv(+bias) followed by eval BatchNorm -> (weight, bias), folded in float64 (model.py:49-52,70-72)."""
+    w = np.asarray(sd[conv + ".weight"], dtype=np.float64)
+    b = np.asarray(sd[conv + ".bias"], dtype=np.float64) if (conv + ".bias") in sd else np.zeros(w.shape[0])
+    if bn is None:
+        return w.astype(np.float32), b.astype(np.float32)
+    g = np.asarray(sd[bn + ".weight"], np.float64)
+    beta = np.asarray(sd[bn + ".bias"], np.float64)
+    mean = np.asarray(sd[bn + ".running_mean"], np.float64)
+    var = np.asarray(sd[bn + ".running_var"], np.float64)
+    scale = g / np.sqrt(var + BN_EPS)
+    return (w * scale[:, None, None, None]).astype(np.float32), ((b - mean) * scale + beta).astype(np.float32)
+
+
+def round_bf16(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).bfloat16().float().numpy()
+
+
+class NetBuilder:
+    """Thin typed wrapper over b200romp_net_add_tensor / add_conv that tracks tensor shapes."""
+
+    def __init__(self, device: int, precision: str, engine: int = _lib.ENGINE_AUTO):
+        assert precision in ("fp32", "bf16")
+        self.lib = _lib.load()
+        self.precision = precision
+        self.act = BF16 if precision == "bf16" else F32
+        self.engine = engine
+        self.net = self.lib.b200romp_net_create(device)
+        if not self.net:
+            raise RuntimeError("b200romp_net_create: " + self.lib.b200romp_last_error().decode())
+        self.shape = {}
+        self.names = {}
+        self.flops_per_frame = 0
+
+    def tensor(self, H, W, Cc, dtype=None, nchw=0, external=0, name=None):
+        dtype = self.act if dtype is None else dtype
+        t = _lib.check(self.lib.b200romp_net_add_tensor(self.net, H, W, Cc, dtype, nchw, external), "add_tensor")
+        self.shape[t] = (H, W, Cc, dtype)
+        if name:
+            self.names[name] = t
+        return t
+
+    def const_tensor(self, hwc: np.ndarray, name=None):
+        a = np.ascontiguousarray(hwc, dtype=np.float32)
+        t = _lib.check(self.lib.b200romp_net_add_const_tensor(self.net, a.shape[0], a.shape[1], a.shape[2], F32,
+                                                              a.ctypes.data_as(C.c_void_p)), "add_const_tensor")
+        self.shape[t] = (a.shape[0], a.shape[1], a.shape[2], F32)
+        if name:
+            self.names[name] = t
+        return t
+
+    def conv(self, x, w, b, *, stride=1, relu=False, res=None, res_c_off=0, res_broadcast=0, up=1, out=None,
+             out_c_off=0, out_dtype=None, in_c_off=0, input_norm=0, pow_channel=-1, engine=None, name=None):
+        cout, cin, k, _ = w.shape
+        H, W, _, _ = self.shape[x]
+        Ho, Wo = ((H + 2 * (k // 2) - k) // stride + 1) * up, ((W + 2 * (k // 2) - k) // stride + 1) * up
+        if out is None:
+            out = self.tensor(Ho, Wo, cout, out_dtype, name=name)
+        d = ConvDesc(x, in_c_off, out, out_c_off, -1 if res is None else res, res_c_off, res_broadcast, cin, cout, k,
+                     stride, int(relu), up, input_norm, pow_channel, self.engine if engine is None else engine)
+        w = np.ascontiguousarray(w, dtype=np.float32)
+        if self.precision == "bf16":
+            w = round_bf16(w)      # both engines then see identical bf16-representable weights
+        bp = None if b is None else np.ascontiguousarray(b, dtype=np.float32)
+        _lib.check(self.lib.b200romp_net_add_conv(
+            self.net, C.byref(d), w.ctypes.data_as(C.POINTER(C.c_float)),
+            None if bp is None else bp.ctypes.data_as(C.POINTER(C.c_float))), "add_conv")
+        self.flops_per_frame += 2 * cout * cin * k * k * (Ho // up) * (Wo // up)
+        return out
+
+    def finalize(self, max_batch):
+        _lib.check(self.lib.b200romp_net_finalize(self.net, max_batch), "net_finalize")
+
+    def describe(self):
+        buf = C.create_string_buffer(1 << 18)
+        self.lib.b200romp_net_describe(self.net, buf, len(buf))
+        return buf.value.decode()
+
+
+def coord_maps(size=128):
+    """get_coord_maps, model.py:8-37 -> [1,2,size,size]; ch0 varies along W, ch1 along H."""
+    r = torch.arange(size, dtype=torch.float32) / (size - 1) * 2 - 1
+    return torch.stack([r.view(1, size).expand(size, size), r.view(size, 1).expand(size, size)])[None].contiguous()
+
+
+def build_romp(sd, device=0, precision="bf16", in_dtype=U8, max_batch=64, engine=_lib.ENGINE_AUTO):
+    """ROMPv1 (HRNet-32 + 3 heads) as a libb200romp conv graph.
+
+    Returns (builder, io) with io = dict(frames=, center_maps=, params_maps=) external tensor ids.
+    """
+    sd = {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in sd.items()}
+    nb = NetBuilder(device, precision, engine)
+    act = nb.act
+
+    def cb(x, conv, bn, **kw):
+        w, b = fold_bn(sd, conv, bn)
+        return nb.conv(x, w, b, **kw)
+
+    frames = nb.tensor(512, 512, 3, in_dtype, external=1, name="frames")
+    p = "backbone."
+    x = cb(frames, p + "conv1", p + "bn1", stride=2, relu=True, input_norm=1, engine=_lib.ENGINE_SIMT)   # model.py:385-387
+    x = cb(x, p + "conv2", p + "bn2", stride=2, relu=True)                                                # :388-390
+    for i in range(4):                                                                                     # layer1, :391
+        q = f"{p}layer1.{i}."
+        y = cb(x, q + "conv1", q + "bn1", relu=True)
+        y = cb(y, q + "conv2", q + "bn2", relu=True)
+        res = cb(x, q + "downsample.0", q + "downsample.1") if (q + "downsample.0.weight") in sd else x
+        x = cb(y, q + "conv3", q + "bn3", relu=True, res=res)
+
+    def basic_block(x, q, in_c_off=0, res_c_off=0):
+        t = cb(x, q + "conv1", q + "bn1", relu=True, in_c_off=in_c_off)
+        return cb(t, q + "conv2", q + "bn2", relu=True, res=x, res_c_off=res_c_off)
+
+    def hr_module(xs, q, nbr, multi=True):
+        """HighResolutionModule.forward model.py:226-244; fuse sum kept in fp32 until the final ReLU."""
+        xs = list(xs)
+        for b in range(nbr):
+            for k in range(4):
+                xs[b] = basic_block(xs[b], f"{q}branches.{b}.{k}.")
+        outs = []
+        for i in range(nbr if multi else 1):
+            acc = xs[i]                       # identity term (model.py:236-239) seeds the running sum
+            terms = [j for j in range(nbr) if j != i]
+            for t_idx, j in enumerate(terms):
+                last = t_idx == len(terms) - 1
+                od = act if last else F32
+                r = f"{q}fuse_layers.{i}.{j}."
+                if j > i:                     # 1x1 conv + BN + nearest upsample (model.py:188-197)
+                    acc = cb(xs[j], r + "0", r + "1", res=acc, up=2 ** (j - i), relu=last, out_dtype=od)
+                else:                         # chain of stride-2 3x3 convs (model.py:200-218)
+                    t = xs[j]
+                    for k in range(i - j - 1):
+                        t = cb(t, f"{r}{k}.0", f"{r}{k}.1", stride=2, relu=True)
+                    k = i - j - 1
+                    acc = cb(t, f"{r}{k}.0", f"{r}{k}.1", stride=2, res=acc, relu=last, out_dtype=od)
+            outs.append(acc)
+        return outs
+
+    xs = [cb(x, p + "transition1.0.0", p + "transition1.0.1", relu=True),                     # model.py:393-398
+          cb(x, p + "transition1.1.0.0", p + "transition1.1.0.1", stride=2, relu=True)]
+    ys = hr_module(xs, p + "stage2.0.", 2)
+    xs = ys + [cb(ys[-1], p + "transition2.2.0.0", p + "transition2.2.0.1", stride=2, relu=True)]   # :401-406
+    for m in range(4):
+        xs = hr_module(xs, f"{p}stage3.{m}.", 3)
+    xs = xs + [cb(xs[-1], p + "transition3.3.0.0", p + "transition3.3.0.1", stride=2, relu=True)]    # :409-414
+    for m in range(3):
+        xs = hr_module(xs, f"{p}stage4.{m}.", 4, multi=(m != 2))
+    feat = xs[0]
+    nb.names["backbone_out"] = feat
+
+    # ---- heads (model.py:445-481).  The three head-in convs 34->64 (3x3, s2, bias, BN, ReLU) are fused into
+    # one 32->192 conv; the two constant coord channels (model.py:473) become a per-pixel bias map.
+    order = (3, 1, 2)                 # cam, params, center  -> channel slices 0, 64, 128 of the fused tensor
+    ws, bs = zip(*[fold_bn(sd, f"final_layers.{h}.0.0", f"final_layers.{h}.0.1") for h in order])
+    w_all, b_all = np.concatenate(ws, 0), np.concatenate(bs, 0)
+    with torch.no_grad():
+        cm = F.conv2d(coord_maps(128), torch.from_numpy(w_all[:, 32:34].copy()), None, stride=2, padding=1)[0]
+    bias_map = (cm + torch.from_numpy(b_all)[:, None, None]).permute(1, 2, 0).contiguous().numpy()   # [64,64,192]
+    bias_t = nb.const_tensor(bias_map, name="head_bias_map")
+    hin = nb.conv(feat, np.ascontiguousarray(w_all[:, :32]), None, stride=2, relu=True, res=bias_t, res_broadcast=1,
+                  name="head_in")
+    center_maps = nb.tensor(64, 64, 1, F32, nchw=1, external=1, name="center_maps")
+    params_maps = nb.tensor(64, 64, 145, F32, nchw=1, external=1, name="params_maps")
+    for s, h in enumerate(order):
+        q = f"final_layers.{h}."
+        y = basic_block(hin, q + "1.0.0.", in_c_off=64 * s, res_c_off=64 * s)
+        y = basic_block(y, q + "1.1.0.")
+        w, b = fold_bn(sd, q + "2", None)
+        if h == 3:      # cam maps -> params_maps[:, 0:3], cam scale 1.1**x (model.py:480, main.py:113)
+            nb.conv(y, w, b, out=params_maps, out_c_off=0, pow_channel=0, engine=_lib.ENGINE_SIMT)
+        elif h == 1:    # params maps -> params_maps[:, 3:145]
+            nb.conv(y, w, b, out=params_maps, out_c_off=3, engine=_lib.ENGINE_SIMT)
+        else:
+            nb.conv(y, w, b, out=center_maps, engine=_lib.ENGINE_SIMT)
+    nb.finalize(max_batch)
+    return nb, dict(frames=frames, center_maps=center_maps, params_maps=params_maps)

@@ -1,0 +1,281 @@
+"""Drop-in call surface of ``simple_romp``'s ROMP for the per-frame inference hot path.
+
+Mirrors simple_romp/romp/main.py: ``romp_settings`` (:17-60, same flags and defaults, minus the
+import-time download side effects), ``class ROMP`` (:64-176) with ``ROMP(settings)(image_bgr) -> dict | None``
+and the same output dict.  ``forward_batch`` is the batched entry point the reference
+lacks (its ``forward`` takes one image per call, main.py:106-107).
+
+Python/PyTorch here only allocates device buffers, owns the CUDA stream and moves bytes; every per-frame
+FLOP runs in libb200romp.so (hand-written sm_100a CUDA).  There is no CPU or PyTorch compute fallback:
+without the library or without a GPU, constructing ``ROMP`` raises.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import os
+import os.path as osp
+import sys
+
+import numpy as np
+import torch
+
+from . import _lib, graph
+from ._lib import BF16, F32, U8
+
+MAX_PERSON = 64          # CenterMap.max_person, post_parser.py:11
+N_PARAMS = 145           # 3 cam + 22*6 rot6d + 10 betas, model.py:429
+
+
+def romp_settings(input_args=sys.argv[1:]):
+    """Same flags/defaults as the reference's romp_settings (main.py:17-60); no downloads, no prints."""
+    parser = argparse.ArgumentParser(description="ROMP (B200-native hot path)")
+    parser.add_argument("-m", "--mode", type=str, default="image")
+    parser.add_argument("-i", "--input", type=str, default=None)
+    parser.add_argument("-o", "--save_path", type=str, default=osp.join(osp.expanduser("~"), "ROMP_results"))
+    parser.add_argument("--GPU", type=int, default=0)
+    parser.add_argument("--onnx", action="store_true")
+    parser.add_argument("-t", "--temporal_optimize", action="store_true")
+    parser.add_argument("--center_thresh", type=float, default=0.25)
+    parser.add_argument("--show_largest", action="store_true")
+    parser.add_argument("-sc", "--smooth_coeff", type=float, default=3.0)
+    parser.add_argument("--calc_smpl", action="store_false")
+    parser.add_argument("--render_mesh", action="store_true")
+    parser.add_argument("--renderer", type=str, default="sim3dr")
+    parser.add_argument("--show", action="store_true")
+    parser.add_argument("--show_items", type=str, default="mesh")
+    parser.add_argument("--save_video", action="store_true")
+    parser.add_argument("--frame_rate", type=int, default=24)
+    parser.add_argument("--smpl_path", type=str, default=osp.join(osp.expanduser("~"), ".romp", "SMPL_NEUTRAL.pth"))
+    parser.add_argument("--model_path", type=str, default=osp.join(osp.expanduser("~"), ".romp", "ROMP.pkl"))
+    parser.add_argument("--model_onnx_path", type=str, default=osp.join(osp.expanduser("~"), ".romp", "ROMP.onnx"))
+    parser.add_argument("--root_align", type=bool, default=False)
+    parser.add_argument("--webcam_id", type=int, default=0)
+    # --- additions of this implementation (the reference has no equivalents)
+    parser.add_argument("--precision", type=str, default="bf16", choices=["bf16", "fp32"],
+                        help="conv arithmetic: bf16 tensor cores (fast) or fp32 CUDA cores (parity)")
+    parser.add_argument("--max_batch", type=int, default=64, help="largest batch forward_batch will be given")
+    args = parser.parse_args(input_args)
+    if not os.path.exists(args.smpl_path):
+        alt = args.smpl_path.replace("SMPL_NEUTRAL.pth", "smpl_packed_info.pth")   # main.py:50-52
+        if os.path.exists(alt):
+            args.smpl_path = alt
+    return args
+
+
+def padding_image(image):
+    """utils.py:16-24."""
+    h, w = image.shape[:2]
+    side = max(h, w)
+    pad = np.zeros((side, side, 3), dtype=np.uint8)
+    top, left = int((side - h) // 2), int((side - w) // 2)
+    pad[top:top + h, left:left + w] = image
+    return pad, np.array([top, top + h, left, left + w, h, w], dtype=np.float32)
+
+
+def img_preprocess(image, input_size=512):
+    """utils.py:26-30 (host side, OpenCV): BGR->RGB, square zero pad, cubic resize; returns uint8 [1,512,512,3]."""
+    import cv2
+    image = cv2.cvtColor(image, cv2.COLOR_BGR2RGB)
+    pad, info = padding_image(image)
+    return cv2.resize(pad, (input_size, input_size), interpolation=cv2.INTER_CUBIC)[None], info
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+class SMPLParser:
+    """Seam S3 (post_parser.SMPL_parser, post_parser.py:116-125) on libb200romp's fused SMPL kernels."""
+
+    def __init__(self, pack, device, n_betas=10, shape_key="shapedirs"):
+        self.lib = _lib.load()
+        g = lambda k, dt: np.ascontiguousarray(pack[k].detach().cpu().numpy() if isinstance(pack[k], torch.Tensor) else pack[k], dtype=dt)
+        self._keep = [g("v_template", np.float32), g(shape_key, np.float32), g("posedirs", np.float32),
+                      g("J_regressor", np.float32), g("weights", np.float32), g("kintree_table", np.int64),
+                      g("extra_joints_index", np.int64), g("J_regressor_extra9", np.float32),
+                      g("J_regressor_h36m17", np.float32)]
+        k = self._keep
+        assert k[0].shape == (6890, 3) and k[1].shape == (6890, 3, n_betas) and k[2].shape == (207, 20670)
+        fp, lp = C.POINTER(C.c_float), C.POINTER(C.c_longlong)
+        a = lambda x, t: x.ctypes.data_as(t)
+        self.h = self.lib.b200romp_smpl_create(device, n_betas, a(k[0], fp), a(k[1], fp), a(k[2], fp), a(k[3], fp),
+                                               a(k[4], fp), a(k[5], lp), a(k[6], lp), a(k[7], fp), a(k[8], fp))
+        if not self.h:
+            raise RuntimeError("b200romp_smpl_create: " + self.lib.b200romp_last_error().decode())
+        self.n_betas = n_betas
+        self.ws_floats = self.lib.b200romp_smpl_workspace_floats()
+        self.faces = torch.from_numpy(np.ascontiguousarray(g("f", np.int64))) if "f" in pack else None
+
+    def forward(self, betas, thetas, n, d_count, root_align, ws, verts, joints, stream):
+        _lib.check(self.lib.b200romp_smpl_forward(self.h, _ptr(betas), betas.shape[1], _ptr(thetas), n,
+                                                  None if d_count is None else _ptr(d_count), int(root_align),
+                                                  _ptr(ws), _ptr(verts), _ptr(joints), C.c_void_p(stream)), "smpl_forward")
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.b200romp_smpl_destroy(self.h)
+        except Exception:
+            pass
+
+
+class ROMP(torch.nn.Module):
+    """``ROMP(settings)(image_bgr)`` - same contract as simple_romp/romp/main.py:64-176."""
+
+    def __init__(self, romp_settings, state_dict=None, smpl_pack=None):
+        super().__init__()
+        self.settings = s = romp_settings
+        if not torch.cuda.is_available() or s.GPU < 0:
+            raise RuntimeError("romp_b200.ROMP needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        for flag in ("onnx", "temporal_optimize", "render_mesh", "show", "show_largest"):
+            if getattr(s, flag, False):
+                raise NotImplementedError(f"--{flag} is outside the B200 hot path (SURVEY.md section 2: out of scope)")
+        self.lib = _lib.load()
+        self.device_index = int(s.GPU)
+        self.tdevice = torch.device("cuda", self.device_index)
+        torch.cuda.set_device(self.tdevice)
+        self.precision = getattr(s, "precision", "bf16")
+        self.max_batch = int(getattr(s, "max_batch", 64))
+        if state_dict is None:
+            state_dict = torch.load(s.model_path, map_location="cpu")          # main.py:75
+        self._nets = {}
+        self._state_dict = state_dict
+        self.stream = torch.cuda.Stream(device=self.tdevice)
+        self.calc_smpl = bool(s.calc_smpl)
+        if self.calc_smpl:
+            if smpl_pack is None:
+                smpl_pack = torch.load(s.smpl_path, map_location="cpu")        # smpl.py:41
+            self.smpl = SMPLParser(smpl_pack, self.device_index)
+        self._alloc(self.max_batch)
+
+    # ------------------------------------------------------------------------------------------
+    def _net(self, in_dtype):
+        if in_dtype not in self._nets:
+            self._nets[in_dtype] = graph.build_romp(self._state_dict, self.device_index, self.precision, in_dtype,
+                                                    self.max_batch)
+        return self._nets[in_dtype]
+
+    def _alloc(self, B):
+        dev, cap = self.tdevice, B * MAX_PERSON
+        f32, i64 = torch.float32, torch.int64
+        self.cap = cap
+        z = lambda *shape, dtype=f32: torch.zeros(*shape, dtype=dtype, device=dev)
+        self.buf = dict(
+            center_maps=z(B, 1, 64, 64), params_maps=z(B, N_PARAMS, 64, 64),
+            count=z(1, dtype=torch.int32), batch_ids=z(cap, dtype=i64), flat_inds=z(cap, dtype=i64),
+            center_confs=z(cap, 1), params_pred=z(cap, N_PARAMS), cam=z(cap, 3), thetas=z(cap, 72), betas=z(cap, 10),
+            center_preds=z(cap, 2, dtype=i64),
+            parse_ws=torch.zeros(int(self.lib.b200romp_parse_workspace_bytes(B)), dtype=torch.uint8, device=dev),
+            cam_trans=z(cap, 3), pj2d_org=z(cap, 71, 2),
+        )
+        if self.calc_smpl:
+            self.buf.update(verts=z(cap, 6890, 3), joints=z(cap, 71, 3), smpl_ws=z(cap, self.smpl.ws_floats))
+        self.count_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def run_maps(self, frames_dev):
+        """Seam S1 only: frames [B,512,512,3] uint8/float32 on the device -> (center_maps, params_maps) views."""
+        B = frames_dev.shape[0]
+        assert frames_dev.is_cuda and frames_dev.is_contiguous() and tuple(frames_dev.shape[1:]) == (512, 512, 3)
+        assert B <= self.max_batch, f"batch {B} > max_batch {self.max_batch}"
+        in_dtype = {torch.uint8: U8, torch.float32: F32}[frames_dev.dtype]
+        nb, io = self._net(in_dtype)
+        lib, sp = self.lib, C.c_void_p(self.stream.cuda_stream)
+        _lib.check(lib.b200romp_net_bind(nb.net, io["frames"], _ptr(frames_dev)))
+        _lib.check(lib.b200romp_net_bind(nb.net, io["center_maps"], _ptr(self.buf["center_maps"])))
+        _lib.check(lib.b200romp_net_bind(nb.net, io["params_maps"], _ptr(self.buf["params_maps"])))
+        _lib.check(lib.b200romp_net_run(nb.net, B, sp), "net_run")
+        return self.buf["center_maps"][:B], self.buf["params_maps"][:B]
+
+    @torch.no_grad()
+    def run_post(self, B, offsets, center_override=None):
+        """Seams S2-S4 on the maps currently in the buffers; everything enqueued on self.stream, no host sync."""
+        b, lib, sp = self.buf, self.lib, C.c_void_p(self.stream.cuda_stream)
+        center = b["center_maps"] if center_override is None else center_override
+        _lib.check(lib.b200romp_parse(_ptr(center), _ptr(b["params_maps"]), B, 64, 10, float(self.settings.center_thresh),
+                                      self.cap, _ptr(b["count"]), _ptr(b["batch_ids"]), _ptr(b["flat_inds"]),
+                                      _ptr(b["center_confs"]), _ptr(b["params_pred"]), _ptr(b["cam"]), _ptr(b["thetas"]),
+                                      _ptr(b["betas"]), _ptr(b["center_preds"]), _ptr(b["parse_ws"]), sp), "parse")
+        cap = B * MAX_PERSON
+        off = (C.c_float * 6)(*[float(v) for v in offsets])
+        if self.calc_smpl:
+            self.smpl.forward(b["betas"], b["thetas"], cap, b["count"], self.settings.root_align, b["smpl_ws"],
+                              b["verts"], b["joints"], self.stream.cuda_stream)
+            _lib.check(lib.b200romp_project(_ptr(b["joints"]), None, _ptr(b["cam"]), cap, _ptr(b["count"]), off,
+                                            _ptr(b["pj2d_org"]), None, None, _ptr(b["cam_trans"]), sp), "project")
+        else:
+            _lib.check(lib.b200romp_project(_ptr(b["joints"]) if "joints" in b else _ptr(b["cam"]), None, _ptr(b["cam"]),
+                                            cap, _ptr(b["count"]), off, None, None, _ptr(b["cam_trans"]), None, sp), "project")
+
+    def collect(self, to_numpy=True):
+        """The single host sync of a batch: person count, then D2H of the N valid rows (utils.py:32-41)."""
+        with torch.cuda.stream(self.stream):
+            self.count_host.copy_(self.buf["count"], non_blocking=True)
+        self.stream.synchronize()
+        n = int(self.count_host.item())
+        if n == 0:
+            return None
+        b = self.buf
+        out = {
+            "cam": b["cam"][:n], "global_orient": b["thetas"][:n, :3], "body_pose": b["thetas"][:n, 3:],
+            "smpl_betas": b["betas"][:n], "smpl_thetas": b["thetas"][:n], "center_preds": b["center_preds"][:n],
+            "center_confs": b["center_confs"][:n], "cam_trans": b["cam_trans"][:n],
+        }
+        if self.calc_smpl:
+            out.update(verts=b["verts"][:n], joints=b["joints"][:n], pj2d_org=b["pj2d_org"][:n])
+        out["pred_batch_ids"] = b["batch_ids"][:n]
+        if to_numpy:
+            with torch.cuda.stream(self.stream):
+                out = {k: v.contiguous().cpu().numpy() for k, v in out.items()}
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward_batch(self, frames, offsets=None, to_numpy=True, center_override=None):
+        """frames: [B,512,512,3] RGB uint8/float32 (torch tensor, pinned host or device, or numpy), already
+        padded+resized like img_preprocess.  Returns the reference's dict plus ``pred_batch_ids`` or None."""
+        if isinstance(frames, np.ndarray):
+            frames = torch.from_numpy(frames)
+        B = frames.shape[0]
+        with torch.cuda.stream(self.stream):
+            fd = frames.to(self.tdevice, non_blocking=True).contiguous()
+            self.run_maps(fd)
+            self.run_post(B, offsets if offsets is not None else [0, 512, 0, 512, 512, 512], center_override)
+        out = self.collect(to_numpy)
+        del fd
+        return out
+
+    @torch.no_grad()
+    def forward(self, image, signal_ID=0, **kwargs):
+        """image: HxWx3 uint8 BGR (cv2.imread).  main.py:160-176."""
+        input_image, pad_info = img_preprocess(image)
+        out = self.forward_batch(torch.from_numpy(input_image), offsets=pad_info)
+        if out is None:
+            print("None person detected")                                       # post_parser.py:139
+            return None
+        out.pop("pred_batch_ids")
+        if not self.calc_smpl:
+            # without SMPL the reference keeps the weak-perspective translation of main.py:166
+            pass
+        return out
+
+
+default_settings = None   # the reference evaluates romp_settings([]) at import (main.py:62); we do not
+
+
+def main():
+    import cv2
+    args = romp_settings()
+    romp = ROMP(args)
+    if args.mode != "image":
+        raise NotImplementedError("video/webcam loops are outside the hot path; call ROMP.forward per frame")
+    outputs = romp(cv2.imread(args.input))
+    if outputs is not None:
+        os.makedirs(args.save_path, exist_ok=True)
+        np.savez(osp.join(args.save_path, osp.splitext(osp.basename(args.input))[0] + ".npz"), results=outputs)
+
+
+if __name__ == "__main__":
+    main()

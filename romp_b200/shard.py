@@ -1,0 +1,81 @@
+"""Frame-sharded multi-GPU execution.
+
+Frames are independent, so rank r simply runs the whole hot path on its contiguous slice of the batch; no
+collective is needed to compute.  The single collective is the all-gather that *collects* the per-person
+outputs: one all_gather of the person counts, then one padded all_gather of a packed float record and one of
+a packed int64 record.  ``pred_batch_ids`` are offset by the rank's first frame (the reference does the same
+bookkeeping for nn.DataParallel: romp/lib/maps_utils/result_parser.py:59-64).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+FLOAT_KEYS = ["cam", "smpl_thetas", "smpl_betas", "center_confs", "cam_trans", "joints", "pj2d_org", "verts"]
+INT_KEYS = ["center_preds", "pred_batch_ids"]
+
+
+def shard_range(total_frames: int, rank: int, world: int):
+    """Contiguous frame range of `rank` (remainder frames go to the first ranks)."""
+    base, rem = divmod(total_frames, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def pack(out, frame_offset, device):
+    """dict (or None) -> (float record [n, F], int record [n, 3], layout)."""
+    if out is None:
+        return torch.zeros(0, 0, device=device), torch.zeros(0, 3, dtype=torch.int64, device=device), None
+    t = {k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v).to(device) for k, v in out.items()}
+    n = t["cam"].shape[0]
+    fkeys = [k for k in FLOAT_KEYS if k in t]
+    layout = [(k, tuple(t[k].shape[1:])) for k in fkeys]
+    frec = torch.cat([t[k].reshape(n, -1).float() for k in fkeys], 1)
+    irec = torch.cat([t["center_preds"].reshape(n, 2), (t["pred_batch_ids"] + frame_offset).reshape(n, 1)], 1)
+    return frec.contiguous(), irec.contiguous(), layout
+
+
+def unpack(frec, irec, layout):
+    out, col = {}, 0
+    n = frec.shape[0]
+    for k, shp in layout:
+        w = int(np.prod(shp)) if len(shp) else 1
+        out[k] = frec[:, col:col + w].reshape((n,) + shp)
+        col += w
+    out["center_preds"] = irec[:, :2]
+    out["pred_batch_ids"] = irec[:, 2]
+    out["global_orient"] = out["smpl_thetas"][:, :3]
+    out["body_pose"] = out["smpl_thetas"][:, 3:]
+    return out
+
+
+def all_gather_outputs(out, frame_offset: int, world: int, to_numpy: bool = True, group=None):
+    """All ranks end up with the outputs of every rank, ordered by (global frame asc, score desc)."""
+    backend = dist.get_backend(group)
+    device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    frec, irec, layout = pack(out, frame_offset, device)
+    n = torch.tensor([frec.shape[0], frec.shape[1]], dtype=torch.int64, device=device)
+    counts = torch.zeros(world * 2, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(counts, n, group=group)
+    counts = counts.cpu().view(world, 2)
+    nmax, width = int(counts[:, 0].max()), int(counts[:, 1].max())
+    if nmax == 0:
+        return None
+    layouts = [None] * world
+    dist.all_gather_object(layouts, layout, group=group)
+    layout = next(l for l in layouts if l is not None)
+    fpad = torch.zeros(nmax, width, device=device)
+    ipad = torch.zeros(nmax, 3, dtype=torch.int64, device=device)
+    if frec.shape[0]:
+        fpad[:frec.shape[0]] = frec
+        ipad[:irec.shape[0]] = irec
+    fall = torch.zeros(world * nmax, width, device=device)
+    iall = torch.zeros(world * nmax, 3, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(fall, fpad, group=group)
+    dist.all_gather_into_tensor(iall, ipad, group=group)
+    keep = torch.cat([torch.arange(r * nmax, r * nmax + int(counts[r, 0])) for r in range(world)]).to(device)
+    res = unpack(fall[keep], iall[keep], layout)
+    if to_numpy:
+        res = {k: v.contiguous().cpu().numpy() for k, v in res.items()}
+    return res

@@ -1,0 +1,113 @@
+"""Whole hot path on the GPU (ROMP call surface) against the CPU oracle, stage-wise as SURVEY 8c prescribes:
+P1 maps, P2 parse on identical maps (bit-exact indices), P3 thetas, P4 SMPL (1e-4), P5 MPJPE."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import romp_oracle as O
+from romp_b200 import ROMP, romp_settings, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def params():
+    return synth.romp_state_dict(0), synth.smpl_pack(0)
+
+
+@pytest.fixture(scope="module")
+def oracle_maps(params):
+    frames = synth.synthetic_frames(2, seed=5)
+    return frames, O.romp_maps(params[0], frames)
+
+
+def make(params, precision, max_batch=2, extra=()):
+    s = romp_settings(["--precision", precision, "--max_batch", str(max_batch), *extra])
+    return ROMP(s, state_dict=params[0], smpl_pack=params[1])
+
+
+def test_p1_maps_fp32_parity(params, oracle_maps):
+    frames, (oc, op) = oracle_maps
+    m = make(params, "fp32")
+    for dt in (torch.uint8, torch.float32):                      # both input dtypes of the stem
+        with torch.cuda.stream(m.stream):
+            c, p = m.run_maps(torch.from_numpy(frames).to(dt).cuda())
+        m.stream.synchronize()
+        ec, ep = (c.cpu() - oc).abs().max().item(), (p.cpu() - op).abs().max().item()
+        print(f"fp32 engine vs oracle: center {ec:.3e} params {ep:.3e}")
+        assert ec < 2e-3 and ep < 5e-3                          # ~100 fp32 layers, different summation order
+    # the backbone feature map itself
+    nb, _ = m._net(0)                           # F32 input net
+    feat = torch.zeros(2, 128, 128, 32, device="cuda")
+    m.lib.b200romp_net_read_tensor(nb.net, nb.names["backbone_out"], 2, feat.data_ptr(), None)
+    torch.cuda.synchronize()
+    of = O.hrnet32_forward(O.to_torch_sd(params[0]), torch.from_numpy(frames).float())
+    assert (feat.cpu().permute(0, 3, 1, 2) - of).abs().max().item() < 5e-3
+
+
+def test_p1_maps_bf16_tolerance(params, oracle_maps):
+    frames, (oc, op) = oracle_maps
+    m = make(params, "bf16")
+    with torch.cuda.stream(m.stream):
+        c, p = m.run_maps(torch.from_numpy(frames).cuda())
+    m.stream.synchronize()
+    ec, ep = (c.cpu() - oc).abs().max().item(), (p.cpu() - op).abs().max().item()
+    print(f"bf16 engine vs fp32 oracle: center max|err| {ec:.3e} (std {oc.std():.3f}) params {ep:.3e} (std {op.std():.3f})")
+    # bf16 storage of every activation through ~100 layers; SURVEY 8c measured 0.072/0.088 for a bf16-autocast
+    # run of the reference itself - we must be in that regime, not better than fp32 and not broken.
+    assert ec < 0.25 * float(oc.std()) + 0.1 and ep < 0.25 * float(op.std()) + 0.3
+    assert np.corrcoef(c.cpu().numpy().ravel(), oc.numpy().ravel())[0, 1] > 0.995
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_p2_to_p5_planted_batch(params, precision):
+    B = 4
+    frames = synth.synthetic_frames(B, seed=9)
+    planted, truth = synth.plant_centers(B, seed=9)
+    m = make(params, precision, max_batch=B)
+    out = m.forward_batch(torch.from_numpy(frames), center_override=torch.from_numpy(planted).cuda())
+    gpu_params = m.buf["params_maps"][:B].cpu()
+    ref = O.parsing_outputs(planted, gpu_params, 0.25)           # identical maps -> indices must be bit-exact
+    n = sum(len(t) for t in truth)
+    assert len(out["cam"]) == n == len(ref["pred_batch_ids"])
+    assert np.array_equal(out["pred_batch_ids"], ref["pred_batch_ids"].numpy())
+    assert np.array_equal(out["center_preds"], ref["center_preds"].numpy())
+    flat = np.concatenate([[f for f, _ in t] for t in truth])
+    assert np.array_equal(out["center_preds"][:, 0] // 8 + out["center_preds"][:, 1] // 8 * 64, flat)
+    assert np.array_equal(out["cam"], ref["cam"].numpy()) and np.array_equal(out["smpl_betas"], ref["smpl_betas"].numpy())
+    assert np.abs(out["smpl_thetas"] - ref["smpl_thetas"].numpy()).max() < 1e-5
+    v, j = O.smpl_forward(params[1], out["smpl_betas"], out["smpl_thetas"])
+    assert np.abs(out["verts"] - v.numpy()).max() < 1e-4 and np.abs(out["joints"] - j.numpy()).max() < 1e-4
+    pr = O.project_outputs(j, None, ref["cam"], [0, 512, 0, 512, 512, 512])
+    assert np.abs(out["pj2d_org"] - pr["pj2d_org"].numpy()).max() < 2e-3
+    assert np.abs(out["cam_trans"] - pr["cam_trans"].numpy()).max() < 2e-3
+    assert set(out.keys()) == {"cam", "global_orient", "body_pose", "smpl_betas", "smpl_thetas", "center_preds",
+                               "center_confs", "cam_trans", "verts", "joints", "pj2d_org", "pred_batch_ids"}
+    assert out["center_confs"].shape == (n, 1) and out["body_pose"].shape == (n, 69) and out["center_preds"].dtype == np.int64
+    # P5: end to end against the fp32 oracle (its own maps for the params, same planted detections)
+    full = O.romp_forward(params[0], params[1], frames, center_override=planted)
+    mp = O.mpjpe_mm(out["joints"], full["joints"])
+    print(f"{precision}: persons {n}  MPJPE vs fp32 oracle {mp:.3f} mm")
+    assert mp < (0.5 if precision == "fp32" else 60.0)
+
+
+def test_nobody_returns_none_and_single_image_forward(params):
+    m = make(params, "fp32", max_batch=1)
+    frames = synth.synthetic_frames(1, seed=5)
+    assert m.forward_batch(torch.from_numpy(frames)) is None      # synthetic weights: no natural detections
+    # single BGR image through the reference-style __call__, non-square -> pad info is used
+    rs = np.random.RandomState(0)
+    img = rs.randint(0, 256, size=(300, 400, 3)).astype(np.uint8)
+    assert m(img) is None
+    import cv2
+    from romp_b200.main import img_preprocess
+    inp, pad = img_preprocess(img)
+    assert inp.shape == (1, 512, 512, 3) and pad.tolist() == [50, 350, 0, 400, 300, 400]
+    planted, _ = synth.plant_centers(1, seed=1)
+    out = m.forward_batch(torch.from_numpy(inp), offsets=pad, center_override=torch.from_numpy(planted).cuda())
+    full = O.romp_maps(params[0], inp)
+    ref = O.parsing_outputs(planted, full[1], 0.25)
+    assert np.array_equal(out["center_preds"], ref["center_preds"].numpy())
+    v, j = O.smpl_forward(params[1], ref["smpl_betas"], ref["smpl_thetas"])
+    pr = O.project_outputs(j, None, ref["cam"], pad)
+    assert np.abs(out["pj2d_org"] - pr["pj2d_org"].numpy()).max() < 0.5   # pixels in the 400x300 original image
