@@ -147,7 +147,7 @@ def run_ours(args):
 
     def gather(out):
         """the single collective of the sharded path: all-gather of the packed per-person outputs"""
-        if world == 1 or out is None:
+        if world == 1:
             return out
         from romp_b200 import shard
         return shard.all_gather_outputs(out, rank * B, world)
