@@ -359,17 +359,24 @@ def to_org_image(kps, offsets):
 
 
 def estimate_translation_lsq(j3d, j2d, focal=443.4, img=512.0):
-    """estimate_translation_np, utils.py:347-389 (unit weights), float64 normal equations, per person."""
-    j3d, j2d = np.asarray(j3d, np.float64), np.asarray(j2d, np.float64)
-    out = np.zeros((j3d.shape[0], 3), np.float32)
-    for i in range(j3d.shape[0]):
-        n = j3d.shape[1]
-        Z = np.repeat(j3d[i, :, 2], 2)
-        XY = j3d[i, :, :2].reshape(-1)
+    """estimate_translation (utils.py:391-436) with the closed-form solver estimate_translation_np
+    (:347-389, unit weights) in place of cv2.solvePnPRansac: validity mask of :404-408,419 (2-D y > -2 and
+    3-D z != -2), fewer than 4 valid joints -> INVALID_TRANS = -1 (:420-422); float64 normal equations."""
+    j3d32, j2d32 = np.asarray(j3d, np.float32), np.asarray(j2d, np.float32)
+    out = np.zeros((j3d32.shape[0], 3), np.float32)
+    for i in range(j3d32.shape[0]):
+        valid = (j2d32[i, :, -1] > -2.0) & (j3d32[i, :, -1] != -2.0)
+        if valid.sum() < 4:
+            out[i] = -1.0
+            continue
+        p3, p2 = j3d32[i][valid].astype(np.float64), j2d32[i][valid].astype(np.float64)
+        n = p3.shape[0]
+        Z = np.repeat(p3[:, 2], 2)
+        XY = p3[:, :2].reshape(-1)
         O = np.tile(np.array([img / 2, img / 2]), n)
         Fv = np.full(2 * n, focal)
-        Q = np.stack([Fv * np.tile([1, 0], n), Fv * np.tile([0, 1], n), O - j2d[i].reshape(-1)], 1)
-        c = (j2d[i].reshape(-1) - O) * Z - Fv * XY
+        Q = np.stack([Fv * np.tile([1, 0], n), Fv * np.tile([0, 1], n), O - p2.reshape(-1)], 1)
+        c = (p2.reshape(-1) - O) * Z - Fv * XY
         out[i] = np.linalg.solve(Q.T @ Q, Q.T @ c)
     return out
 

@@ -1,8 +1,421 @@
-// placeholder: replaced by the tcgen05 implementation
+// tcgen05 implicit-GEMM convolution engine for sm_100a (the dominant kernel of the hot path).
+//
+// Replaces, per layer, cuDNN Conv2d + separate BatchNorm/ReLU/add/Upsample kernels of the reference
+// (simple_romp/romp/model.py:49-123,185-244) for 3x3-stride-1 and 1x1 convolutions with
+// Cin in {32,64,128,256} on NHWC bf16 activations (fp32 accumulate in TMEM).
+//
+// Mapping (im2col-free):
+//   GEMM M = 128 output pixels = one 16x8 spatial tile of one frame          (UMMA_M = 128, cta_group::1)
+//   GEMM N = NT output channels (32 or 64) per CTA, weights RESIDENT in shared memory for the CTA's
+//            lifetime (persistent CTAs loop over pixel tiles) - streaming them would cost 64 B/clk/SM
+//   GEMM K = taps x Cin, walked as (64-channel chunk) x (tap) x (16-channel UMMA_K step)
+//   A operand: ONE TMA load per (tile, chunk) brings the (16+2)x(8+2) halo tile, channels innermost,
+//            hardware-swizzled (128B, or 64B for Cin=32).  The 9 taps are 9 *shifted shared-memory
+//            descriptors* into that same halo tile: start address + (r*10+s) pixel rows, stride-byte-offset
+//            = 10 pixel rows (one image row of the halo), so the input is read from L2 once, not 9 times.
+//            Zero padding comes from TMA out-of-bounds fill (negative start coordinates).
+//   D: fp32 accumulators in TMEM, double buffered (2 x NT columns) so the epilogue of tile i overlaps the
+//            MMAs of tile i+1.
+//   Epilogue (4 warps, one TMEM lane quarter each): tcgen05.ld 32x32b -> +bias -> residual / ReLU /
+//            nearest-upsample replication / dtype conversion (shared conv_epilogue_store) -> global.
+// Warp roles: warp0 = TMA producer, warp1 = TMEM allocator + single-thread MMA issuer, warps2-5 = epilogue.
+// Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), persistent tile loop.
+#include <cuda.h>
+
+#include <mutex>
+
 #include "conv_tc.cuh"
+
 namespace b200romp {
-std::string TcConvPlan::describe() const { return ""; }
-bool tc_conv_supported(const ConvParams&, int, int) { return false; }
-int tc_conv_prepare(const ConvParams&, int, int, const float*, int, TcConvPlan*, std::vector<void*>*) { return B200ROMP_EINVAL; }
-int tc_conv_launch(const TcConvPlan&, const ConvParams&, cudaStream_t) { return B200ROMP_EINVAL; }
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must not hang the GPU box - trap after ~2 s instead.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("b200romp conv_tc: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, K-major, swizzled (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
+//   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 | [46,48) version=1 |
+//   [49,52) base offset = 0 (pattern anchored at 1024 B) | [61,64) layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t sbo_bytes, uint32_t layout) {
+  return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)layout << 61);
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------------
+template <int KS, int CIN, int NT, bool PER_TAP>
+struct TcCfg {
+  static constexpr int TAPS = KS * KS;
+  static constexpr int PAD = KS / 2;
+  static constexpr int CW = CIN < 64 ? CIN : 64;       // channels per chunk = one swizzle row
+  static constexpr int KCH = CIN / CW;
+  static constexpr int ROWB = CW * 2;                  // bytes per pixel row in smem (64 or 128)
+  static constexpr int LAYOUT = ROWB == 128 ? 2 : 4;   // SWIZZLE_128B / SWIZZLE_64B
+  static constexpr int HW_ = PER_TAP ? 8 : 8 + 2 * PAD;
+  static constexpr int HH = PER_TAP ? 16 : 16 + 2 * PAD;
+  static constexpr int LOADS_PER_CHUNK = PER_TAP ? TAPS : 1;
+  static constexpr int STAGE_PAYLOAD = HH * HW_ * ROWB;
+  static constexpr int STAGE_BYTES = (STAGE_PAYLOAD + 1023) / 1024 * 1024;
+  static constexpr int BTILE = NT * ROWB;
+  static constexpr int B_BYTES = TAPS * KCH * BTILE;
+  static constexpr int TMEM_COLS = 2 * NT <= 32 ? 32 : (2 * NT <= 64 ? 64 : (2 * NT <= 128 ? 128 : 256));
+  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+};
+
+template <int KS, int CIN, int NT, bool PER_TAP>
+__global__ void __launch_bounds__(192, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, const uint8_t* __restrict__ wpack,
+               int tiles_x, int tiles_y, int num_tiles, int stages) {
+  using Cfg = TcCfg<KS, CIN, NT, PER_TAP>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sB = smem;
+  uint8_t* sA = smem + Cfg::B_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sA + (size_t)stages * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + stages;
+  uint64_t* b_full = empty + stages;
+  uint64_t* tmem_full = b_full + 1;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(b_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int per_frame = tiles_x * tiles_y;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(b_full, Cfg::B_BYTES);
+      const uint8_t* wsrc = wpack + (size_t)blockIdx.y * Cfg::B_BYTES;
+      for (int i = 0; i < Cfg::TAPS * Cfg::KCH; ++i)
+        bulk_copy_g2s(sB + (size_t)i * Cfg::BTILE, wsrc + (size_t)i * Cfg::BTILE, Cfg::BTILE, b_full);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n = tile / per_frame, rem = tile % per_frame;
+        const int y0 = (rem / tiles_x) * 16, x0 = (rem % tiles_x) * 8;
+        for (int c = 0; c < Cfg::KCH; ++c) {
+          for (int l = 0; l < Cfg::LOADS_PER_CHUNK; ++l) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_PAYLOAD);
+            const int dy = PER_TAP ? l / KS - Cfg::PAD : -Cfg::PAD;
+            const int dx = PER_TAP ? l % KS - Cfg::PAD : -Cfg::PAD;
+            tma_load_4d(sA + (size_t)stage * Cfg::STAGE_BYTES, &tmap, &full[stage], c * Cfg::CW, x0 + dx, y0 + dy, n);
+            if (++stage == stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      mbar_wait(b_full, 0);
+      tc_fence_after();
+      const uint32_t b_base = smem_u32(sB);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NT);
+        uint32_t accumulate = 0;
+        for (int c = 0; c < Cfg::KCH; ++c) {
+          for (int l = 0; l < Cfg::LOADS_PER_CHUNK; ++l) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(sA + (size_t)stage * Cfg::STAGE_BYTES);
+            const int t_lo = PER_TAP ? l : 0, t_hi = PER_TAP ? l + 1 : Cfg::TAPS;
+            for (int t = t_lo; t < t_hi; ++t) {
+              const int r = t / KS, s = t % KS;
+              const uint32_t a_tap = PER_TAP ? a_base : a_base + (uint32_t)((r * Cfg::HW_ + s) * Cfg::ROWB);
+              const uint32_t b_tap = b_base + (uint32_t)((t * Cfg::KCH + c) * Cfg::BTILE);
+#pragma unroll
+              for (int k = 0; k < Cfg::CW / 16; ++k) {
+                const uint64_t adesc = make_smem_desc(a_tap + k * 32, Cfg::HW_ * Cfg::ROWB, Cfg::LAYOUT);
+                const uint64_t bdesc = make_smem_desc(b_tap + k * 32, 8 * Cfg::ROWB, Cfg::LAYOUT);
+                umma_bf16(d_tmem, adesc, bdesc, Cfg::IDESC, accumulate);
+                accumulate = 1;
+              }
+            }
+            umma_commit(&empty[stage]);          // smem stage reusable once these MMAs retire
+            if (++stage == stages) { stage = 0; phase ^= 1; }
+          }
+        }
+        umma_commit(&tmem_full[acc]);            // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;                 // GEMM row = pixel within the 16x8 tile
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int co0 = blockIdx.y * NT;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n = tile / per_frame, rem = tile % per_frame;
+      const int oy = (rem / tiles_x) * 16 + (m >> 3), ox = (rem % tiles_x) * 8 + (m & 7);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT);
+#pragma unroll
+      for (int c0 = 0; c0 < NT; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c0, r);
+        tmem_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + __ldg(&p.bias[co0 + c0 + j]);
+        conv_epilogue_store<16>(p, n, oy, ox, co0 + c0, v);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  });
+  return fn;
+}
+
+static bool tc_per_tap() {
+  const char* e = getenv("B200ROMP_TC_PER_TAP");
+  return e && e[0] == '1';
+}
+
+std::string TcConvPlan::describe() const {
+  char buf[96];
+  snprintf(buf, sizeof(buf), " [tc k%d nt%d grid %dx%d smem %d stages %d]", kind / 10, nt, grid_x, grid_y, smem_bytes, stages);
+  return buf;
+}
+
+bool tc_conv_supported(const ConvParams& p, int ksize, int stride) {
+  if (stride != 1 || (ksize != 1 && ksize != 3)) return false;
+  if (p.in_dtype != B200ROMP_BF16 || p.input_norm || p.out_nchw || p.pow_channel >= 0) return false;
+  if (p.cin != 32 && p.cin != 64 && p.cin != 128 && p.cin != 256) return false;
+  if (p.cout % 32 != 0) return false;
+  if (p.Hout % 16 != 0 || p.Wout % 8 != 0) return false;
+  if (p.in_C % 8 != 0 || p.in_c_off % 8 != 0) return false;             // TMA: 16 B aligned base and strides
+  if ((reinterpret_cast<uintptr_t>(p.in) & 15) != 0) return false;
+  return true;
+}
+
+template <int KS, int CIN, int NT, bool PER_TAP>
+static int launch_inst(const TcConvPlan& plan, const ConvParams& p, cudaStream_t stream, bool set_attr_only) {
+  auto kern = conv_tc_kernel<KS, CIN, NT, PER_TAP>;
+  if (set_attr_only) {
+    B2R_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
+    return B200ROMP_OK;
+  }
+  CUtensorMap tm;
+  memcpy(&tm, plan.tmap_in, sizeof(tm));
+  const int tiles_x = p.Wout / 8, tiles_y = p.Hout / 16;
+  const int num_tiles = tiles_x * tiles_y * p.B;
+  dim3 grid(std::min(plan.grid_x, num_tiles), plan.grid_y);
+  kern<<<grid, 192, plan.smem_bytes, stream>>>(tm, p, reinterpret_cast<const uint8_t*>(plan.d_wpack), tiles_x, tiles_y,
+                                               num_tiles, plan.stages);
+  B2R_CUDA_OK(cudaGetLastError());
+  return B200ROMP_OK;
+}
+
+template <bool PER_TAP>
+static int dispatch(const TcConvPlan& plan, const ConvParams& p, cudaStream_t stream, bool attr) {
+  const int ks = plan.kind / 10;
+#define B2R_CASE(K, C, N) \
+  if (ks == K && plan.cin == C && plan.nt == N) return launch_inst<K, C, N, PER_TAP>(plan, p, stream, attr);
+  B2R_CASE(3, 32, 32) B2R_CASE(3, 64, 64) B2R_CASE(3, 128, 64) B2R_CASE(3, 256, 32)
+  B2R_CASE(1, 64, 32) B2R_CASE(1, 64, 64) B2R_CASE(1, 128, 32) B2R_CASE(1, 128, 64) B2R_CASE(1, 256, 32)
+  B2R_CASE(1, 256, 64)
+#undef B2R_CASE
+  set_error("conv_tc: no instantiation for k%d cin%d nt%d", ks, plan.cin, plan.nt);
+  return B200ROMP_EINVAL;
+}
+
+int tc_conv_prepare(const ConvParams& p, int ksize, int stride, const float* w_oihw, int sm_count, TcConvPlan* plan,
+                    std::vector<void*>* allocs) {
+  (void)stride;
+  PFN_encodeTiled encode = get_encode();
+  if (!encode) {
+    set_error("conv_tc: cuTensorMapEncodeTiled is unavailable");
+    return B200ROMP_ECUDA;
+  }
+  const bool per_tap = tc_per_tap();
+  const int taps = ksize * ksize;
+  const int cw = p.cin < 64 ? p.cin : 64, kch = p.cin / cw, rowb = cw * 2;
+  // N tile: weights must stay resident next to >= 2 pipeline stages
+  int nt = (p.cout % 64 == 0) ? 64 : 32;
+  const int hh = per_tap ? 16 : 16 + 2 * (ksize / 2), hw = per_tap ? 8 : 8 + 2 * (ksize / 2);
+  const int stage_bytes = (hh * hw * rowb + 1023) / 1024 * 1024;
+  const int budget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/;
+  auto bbytes = [&](int n) { return taps * kch * n * rowb; };
+  if (bbytes(nt) + 3 * stage_bytes > budget && nt == 64) nt = 32;
+  if (bbytes(nt) + 2 * stage_bytes > budget) {
+    set_error("conv_tc: k%d cin%d does not fit shared memory", ksize, p.cin);
+    return B200ROMP_EINVAL;
+  }
+  int stages = (budget - bbytes(nt)) / stage_bytes;
+  stages = std::min(stages, per_tap ? 12 : 6);
+  plan->kind = ksize * 10 + (per_tap ? 1 : 0);
+  plan->cin = p.cin; plan->cout = p.cout; plan->nt = nt; plan->stages = stages;
+  plan->grid_y = p.cout / nt;
+  plan->grid_x = std::max(1, sm_count / plan->grid_y);
+  plan->smem_bytes = bbytes(nt) + stages * stage_bytes + 256 + 1024;
+  // ---- weights -> bf16 shared-memory image [ntile][tap][chunk][NT rows x ROWB], swizzled like TMA would
+  std::vector<__nv_bfloat16> img((size_t)plan->grid_y * taps * kch * nt * cw);
+  for (int j = 0; j < plan->grid_y; ++j)
+    for (int t = 0; t < taps; ++t)
+      for (int c = 0; c < kch; ++c) {
+        __nv_bfloat16* tile = img.data() + (((size_t)j * taps + t) * kch + c) * nt * cw;
+        for (int n = 0; n < nt; ++n)
+          for (int k = 0; k < cw; ++k) {
+            const int co = j * nt + n, ci = c * cw + k;
+            const float w = w_oihw[((size_t)co * p.cin + ci) * taps + t];
+            const int chunk16 = k / 8;
+            const int phase = rowb == 128 ? (n & 7) : ((n >> 1) & 3);     // Swizzle<3,4,3> / Swizzle<2,4,3>
+            const size_t byte = (size_t)n * rowb + (size_t)((chunk16 ^ phase) * 16) + (k % 8) * 2;
+            tile[byte / 2] = __float2bfloat16_rn(w);
+          }
+      }
+  B2R_CUDA_OK(cudaMalloc(&plan->d_wpack, img.size() * sizeof(__nv_bfloat16)));
+  allocs->push_back(plan->d_wpack);
+  B2R_CUDA_OK(cudaMemcpy(plan->d_wpack, img.data(), img.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+  // ---- tensor map over the NHWC input: dims (C slice, W, H, N), halo box, OOB -> zeros
+  CUtensorMap tm;
+  const cuuint64_t gdim[4] = {(cuuint64_t)p.cin, (cuuint64_t)p.Win, (cuuint64_t)p.Hin, (cuuint64_t)p.B};
+  const cuuint64_t gstr[3] = {(cuuint64_t)p.in_C * 2, (cuuint64_t)p.Win * p.in_C * 2, (cuuint64_t)p.Hin * p.Win * p.in_C * 2};
+  const cuuint32_t box[4] = {(cuuint32_t)cw, (cuuint32_t)hw, (cuuint32_t)hh, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  void* base = const_cast<void*>(static_cast<const void*>(static_cast<const __nv_bfloat16*>(p.in) + p.in_c_off));
+  CUresult cr = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    set_error("conv_tc: cuTensorMapEncodeTiled failed with %d", (int)cr);
+    return B200ROMP_ECUDA;
+  }
+  memcpy(plan->tmap_in, &tm, sizeof(tm));
+  return per_tap ? dispatch<true>(*plan, p, nullptr, true) : dispatch<false>(*plan, p, nullptr, true);
+}
+
+int tc_conv_launch(const TcConvPlan& plan, const ConvParams& p, cudaStream_t stream) {
+  return (plan.kind % 10) ? dispatch<true>(plan, p, stream, false) : dispatch<false>(plan, p, stream, false);
+}
+
+}  // namespace b200romp

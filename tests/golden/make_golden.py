@@ -125,6 +125,18 @@ def main():
                 verts_sel=v[:, vsel].numpy(),
                 cam_trans_weak=ref["romp.utils"].convert_cam_to_3d_trans(torch.from_numpy(cam)).numpy(),
             )
+            # ---- G5b: the reference's own closed-form fallback (utils.py:429-434): force the cv2 path to raise so
+            # estimate_translation() runs estimate_translation_np, incl. its validity mask, on partly off-screen people
+            U = ref["romp.utils"]
+            cam2 = cam.copy(); cam2[:, 2] -= np.array([0.0, 1.2, 1.6, 2.5, 0.4], np.float32)   # push people off the top
+            pj = U.batch_orth_proj(j, torch.from_numpy(cam2), mode='2d')
+            j3 = j[:, :24].contiguous().numpy(); p2 = (pj[:, :24, :2].numpy() + 1) * 256
+            orig = U.estimate_translation_cv2
+            def boom(*a, **k): raise RuntimeError("forced")
+            U.estimate_translation_cv2 = boom
+            lsq = U.estimate_translation(j3, p2, focal_length=443.4, img_size=np.array([512, 512])).numpy()
+            U.estimate_translation_cv2 = orig
+            np.savez_compressed(os.path.join(HERE, "cam_trans_lsq.npz"), joints=j.numpy(), cam=cam2, cam_trans_np=lsq)
     print("golden fixtures written to", HERE)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

@@ -151,3 +151,20 @@ def test_project_golden(golden_dir):
     assert np.abs(weak.cpu().numpy() - z["cam_trans_weak"]).max() < 1e-5
     ref = O.project_outputs(torch.from_numpy(z["joints"]), None, z["cam"], z["offsets"])
     assert np.abs(lsq.cpu().numpy() - ref["cam_trans"].numpy()).max() < 1e-3
+
+
+def test_cam_trans_lsq_matches_reference_fallback(golden_dir):
+    """GPU closed-form cam_trans vs the reference's estimate_translation_np path (forced), incl. masked joints and
+    the INVALID_TRANS (-1) rows for people with < 4 visible joints."""
+    z = np.load(os.path.join(golden_dir, "cam_trans_lsq.npz"))
+    lib = _lib.load()
+    n = z["joints"].shape[0]
+    joints = torch.from_numpy(z["joints"]).cuda(); cam = torch.from_numpy(z["cam"]).cuda()
+    lsq = torch.zeros(n, 3, device="cuda")
+    off = (C.c_float * 6)(0, 512, 0, 512, 512, 512)
+    _lib.check(lib.b200romp_project(P(joints), None, P(cam), n, None, off, None, None, None, P(lsq),
+                                    C.c_void_p(torch.cuda.current_stream().cuda_stream)), "project")
+    torch.cuda.synchronize()
+    ref = z["cam_trans_np"]
+    assert (ref == -1).all(1).sum() == 2
+    assert np.abs(lsq.cpu().numpy() - ref).max() < 1e-3
