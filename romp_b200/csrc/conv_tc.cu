@@ -14,111 +14,19 @@
 //            descriptors* into that same halo tile: start address + (r*10+s) pixel rows, stride-byte-offset
 //            = 10 pixel rows (one image row of the halo), so the input is read from L2 once, not 9 times.
 //            Zero padding comes from TMA out-of-bounds fill (negative start coordinates).
-//   D: fp32 accumulators in TMEM, double buffered (2 x NT columns) so the epilogue of tile i overlaps the
-//            MMAs of tile i+1.
-//   Epilogue (4 warps, one TMEM lane quarter each): tcgen05.ld 32x32b -> +bias -> residual / ReLU /
-//            nearest-upsample replication / dtype conversion (shared conv_epilogue_store) -> global.
-// Warp roles: warp0 = TMA producer, warp1 = TMEM allocator + single-thread MMA issuer, warps2-5 = epilogue.
+//   D: fp32 accumulators in TMEM, ring of 4 (4 x NT columns) so epilogues overlap the MMAs of later tiles.
+//   Epilogue (2 groups x 4 warps, one TMEM lane quarter per warp, groups alternate tiles): tcgen05.ld 32x32b.x32
+//            -> +bias (smem) -> residual / ReLU / nearest-upsample replication / dtype conversion with batched
+//            16-byte global accesses.
+// Warp roles: warp0 = TMA producer, warp1 = TMEM allocator + single-thread MMA issuer, warps2-9 = epilogue.
 // Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), persistent tile loop.
-#include <cuda.h>
-
 #include <mutex>
 
 #include "conv_tc.cuh"
+#include "tc_device.cuh"
 
 namespace b200romp {
 
-// ------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.b32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must not hang the GPU box - trap after ~2 s instead.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("b200romp conv_tc: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// Shared-memory matrix descriptor, K-major, swizzled (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
-//   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 | [46,48) version=1 |
-//   [49,52) base offset = 0 (pattern anchored at 1024 B) | [61,64) layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t sbo_bytes, uint32_t layout) {
-  return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | ((uint64_t)1 << 46) |
-         ((uint64_t)layout << 61);
-}
-
-// ------------------------------------------------------------------------------------------------
-// kernel
-// ------------------------------------------------------------------------------------------------
 template <int KS, int CIN, int NT, bool PER_TAP>
 struct TcCfg {
   static constexpr int TAPS = KS * KS;
@@ -134,12 +42,12 @@ struct TcCfg {
   static constexpr int STAGE_BYTES = (STAGE_PAYLOAD + 1023) / 1024 * 1024;
   static constexpr int BTILE = NT * ROWB;
   static constexpr int B_BYTES = TAPS * KCH * BTILE;
-  static constexpr int TMEM_COLS = 2 * NT <= 32 ? 32 : (2 * NT <= 64 ? 64 : (2 * NT <= 128 ? 128 : 256));
+  static constexpr int TMEM_COLS = kAccStages * NT <= 128 ? 128 : 256;
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
 };
 
 template <int KS, int CIN, int NT, bool PER_TAP>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, const uint8_t* __restrict__ wpack,
                int tiles_x, int tiles_y, int num_tiles, int stages) {
   using Cfg = TcCfg<KS, CIN, NT, PER_TAP>;
@@ -151,8 +59,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, con
   uint64_t* empty = full + stages;
   uint64_t* b_full = empty + stages;
   uint64_t* tmem_full = b_full + 1;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* tmem_empty = tmem_full + kAccStages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + kAccStages);
+  float* s_bias = reinterpret_cast<float*>(tmem_ptr + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -161,12 +70,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, con
       mbar_init(&empty[i], 1);
     }
     mbar_init(b_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kAccStages; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 4);
     }
     fence_barrier_init();
   }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + NT) s_bias[threadIdx.x - 64] = p.bias[blockIdx.y * NT + threadIdx.x - 64];
   if (warp == 1) tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -204,10 +114,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, con
       mbar_wait(b_full, 0);
       tc_fence_after();
       const uint32_t b_base = smem_u32(sB);
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & (kAccStages - 1);
+        mbar_wait(&tmem_empty[acc], ((it / kAccStages) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NT);
         uint32_t accumulate = 0;
@@ -234,37 +146,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, con
           }
         }
         umma_commit(&tmem_full[acc]);            // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
-    // ===================== epilogue warps =====================
-    const int q = warp & 3;                      // TMEM lane quarter this warp may access
-    const int m = q * 32 + lane;                 // GEMM row = pixel within the 16x8 tile
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    const int co0 = blockIdx.y * NT;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int n = tile / per_frame, rem = tile % per_frame;
-      const int oy = (rem / tiles_x) * 16 + (m >> 3), ox = (rem % tiles_x) * 8 + (m & 7);
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT);
-#pragma unroll
-      for (int c0 = 0; c0 < NT; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + c0, r);
-        tmem_ld_wait();
-        float v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + __ldg(&p.bias[co0 + c0 + j]);
-        conv_epilogue_store<16>(p, n, oy, ox, co0 + c0, v);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
+    tc_epilogue_loop<NT>(p, tmem_base, tmem_full, tmem_empty, s_bias, tiles_x, per_frame, num_tiles);
   }
   tc_fence_before();
   __syncthreads();
@@ -278,11 +163,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, con
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled get_encode() {
+PFN_encodeTiled tc_get_encode() {
   static PFN_encodeTiled fn = nullptr;
   static std::once_flag once;
   std::call_once(once, [] {
@@ -295,6 +176,29 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
+int tc_pack_weights(const float* w_oihw, int cin, int cout, int taps, int nt, void** d_out, std::vector<void*>* allocs) {
+  const int cw = cin < 64 ? cin : 64, kch = cin / cw, rowb = cw * 2, ntiles = cout / nt;
+  std::vector<__nv_bfloat16> img((size_t)ntiles * taps * kch * nt * cw);
+  for (int j = 0; j < ntiles; ++j)
+    for (int t = 0; t < taps; ++t)
+      for (int c = 0; c < kch; ++c) {
+        __nv_bfloat16* tile = img.data() + (((size_t)j * taps + t) * kch + c) * nt * cw;
+        for (int n = 0; n < nt; ++n)
+          for (int k = 0; k < cw; ++k) {
+            const int co = j * nt + n, ci = c * cw + k;
+            const float w = w_oihw[((size_t)co * cin + ci) * taps + t];
+            const int chunk16 = k / 8;
+            const int phase = rowb == 128 ? (n & 7) : ((n >> 1) & 3);     // Swizzle<3,4,3> / Swizzle<2,4,3>
+            const size_t byte = (size_t)n * rowb + (size_t)((chunk16 ^ phase) * 16) + (k % 8) * 2;
+            tile[byte / 2] = __float2bfloat16_rn(w);
+          }
+      }
+  B2R_CUDA_OK(cudaMalloc(d_out, img.size() * sizeof(__nv_bfloat16)));
+  allocs->push_back(*d_out);
+  B2R_CUDA_OK(cudaMemcpy(*d_out, img.data(), img.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+  return B200ROMP_OK;
+}
+
 static bool tc_per_tap() {
   const char* e = getenv("B200ROMP_TC_PER_TAP");
   return e && e[0] == '1';
@@ -302,17 +206,20 @@ static bool tc_per_tap() {
 
 std::string TcConvPlan::describe() const {
   char buf[96];
-  snprintf(buf, sizeof(buf), " [tc k%d nt%d grid %dx%d smem %d stages %d]", kind / 10, nt, grid_x, grid_y, smem_bytes, stages);
+  snprintf(buf, sizeof(buf), " [tc k%d v%d nt%d grid %dx%d smem %d stages %d]", kind / 10, kind % 10, nt, grid_x, grid_y, smem_bytes, stages);
   return buf;
 }
 
 bool tc_conv_supported(const ConvParams& p, int ksize, int stride) {
+  if (stride == 2 && ksize == 3) return tc_s2_supported(p);
   if (stride != 1 || (ksize != 1 && ksize != 3)) return false;
   if (p.in_dtype != B200ROMP_BF16 || p.input_norm || p.out_nchw || p.pow_channel >= 0) return false;
   if (p.cin != 32 && p.cin != 64 && p.cin != 128 && p.cin != 256) return false;
   if (p.cout % 32 != 0) return false;
   if (p.Hout % 16 != 0 || p.Wout % 8 != 0) return false;
   if (p.in_C % 8 != 0 || p.in_c_off % 8 != 0) return false;             // TMA: 16 B aligned base and strides
+  if (p.out_C % 8 != 0 || p.out_c_off % 8 != 0) return false;           // 16 B vector epilogue
+  if (p.res != nullptr && (p.res_C % 8 != 0 || p.res_c_off % 8 != 0)) return false;
   if ((reinterpret_cast<uintptr_t>(p.in) & 15) != 0) return false;
   return true;
 }
@@ -329,7 +236,7 @@ static int launch_inst(const TcConvPlan& plan, const ConvParams& p, cudaStream_t
   const int tiles_x = p.Wout / 8, tiles_y = p.Hout / 16;
   const int num_tiles = tiles_x * tiles_y * p.B;
   dim3 grid(std::min(plan.grid_x, num_tiles), plan.grid_y);
-  kern<<<grid, 192, plan.smem_bytes, stream>>>(tm, p, reinterpret_cast<const uint8_t*>(plan.d_wpack), tiles_x, tiles_y,
+  kern<<<grid, kTcThreads, plan.smem_bytes, stream>>>(tm, p, reinterpret_cast<const uint8_t*>(plan.d_wpack), tiles_x, tiles_y,
                                                num_tiles, plan.stages);
   B2R_CUDA_OK(cudaGetLastError());
   return B200ROMP_OK;
@@ -350,8 +257,8 @@ static int dispatch(const TcConvPlan& plan, const ConvParams& p, cudaStream_t st
 
 int tc_conv_prepare(const ConvParams& p, int ksize, int stride, const float* w_oihw, int sm_count, TcConvPlan* plan,
                     std::vector<void*>* allocs) {
-  (void)stride;
-  PFN_encodeTiled encode = get_encode();
+  if (stride == 2) return tc_s2_prepare(p, w_oihw, sm_count, plan, allocs);
+  PFN_encodeTiled encode = tc_get_encode();
   if (!encode) {
     set_error("conv_tc: cuTensorMapEncodeTiled is unavailable");
     return B200ROMP_ECUDA;
@@ -363,7 +270,7 @@ int tc_conv_prepare(const ConvParams& p, int ksize, int stride, const float* w_o
   int nt = (p.cout % 64 == 0) ? 64 : 32;
   const int hh = per_tap ? 16 : 16 + 2 * (ksize / 2), hw = per_tap ? 8 : 8 + 2 * (ksize / 2);
   const int stage_bytes = (hh * hw * rowb + 1023) / 1024 * 1024;
-  const int budget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/;
+  const int budget = 227 * 1024 - 1024 /*align slack*/ - 1024 /*barriers + bias*/;
   auto bbytes = [&](int n) { return taps * kch * n * rowb; };
   if (bbytes(nt) + 3 * stage_bytes > budget && nt == 64) nt = 32;
   if (bbytes(nt) + 2 * stage_bytes > budget) {
@@ -376,26 +283,9 @@ int tc_conv_prepare(const ConvParams& p, int ksize, int stride, const float* w_o
   plan->cin = p.cin; plan->cout = p.cout; plan->nt = nt; plan->stages = stages;
   plan->grid_y = p.cout / nt;
   plan->grid_x = std::max(1, sm_count / plan->grid_y);
-  plan->smem_bytes = bbytes(nt) + stages * stage_bytes + 256 + 1024;
-  // ---- weights -> bf16 shared-memory image [ntile][tap][chunk][NT rows x ROWB], swizzled like TMA would
-  std::vector<__nv_bfloat16> img((size_t)plan->grid_y * taps * kch * nt * cw);
-  for (int j = 0; j < plan->grid_y; ++j)
-    for (int t = 0; t < taps; ++t)
-      for (int c = 0; c < kch; ++c) {
-        __nv_bfloat16* tile = img.data() + (((size_t)j * taps + t) * kch + c) * nt * cw;
-        for (int n = 0; n < nt; ++n)
-          for (int k = 0; k < cw; ++k) {
-            const int co = j * nt + n, ci = c * cw + k;
-            const float w = w_oihw[((size_t)co * p.cin + ci) * taps + t];
-            const int chunk16 = k / 8;
-            const int phase = rowb == 128 ? (n & 7) : ((n >> 1) & 3);     // Swizzle<3,4,3> / Swizzle<2,4,3>
-            const size_t byte = (size_t)n * rowb + (size_t)((chunk16 ^ phase) * 16) + (k % 8) * 2;
-            tile[byte / 2] = __float2bfloat16_rn(w);
-          }
-      }
-  B2R_CUDA_OK(cudaMalloc(&plan->d_wpack, img.size() * sizeof(__nv_bfloat16)));
-  allocs->push_back(plan->d_wpack);
-  B2R_CUDA_OK(cudaMemcpy(plan->d_wpack, img.data(), img.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+  plan->smem_bytes = bbytes(nt) + stages * stage_bytes + 1024 + 1024;
+  int rcw = tc_pack_weights(w_oihw, p.cin, p.cout, taps, nt, &plan->d_wpack, allocs);
+  if (rcw) return rcw;
   // ---- tensor map over the NHWC input: dims (C slice, W, H, N), halo box, OOB -> zeros
   CUtensorMap tm;
   const cuuint64_t gdim[4] = {(cuuint64_t)p.cin, (cuuint64_t)p.Win, (cuuint64_t)p.Hin, (cuuint64_t)p.B};
@@ -415,6 +305,7 @@ int tc_conv_prepare(const ConvParams& p, int ksize, int stride, const float* w_o
 }
 
 int tc_conv_launch(const TcConvPlan& plan, const ConvParams& p, cudaStream_t stream) {
+  if (plan.kind % 10 == 2) return tc_s2_launch(plan, p, stream);
   return (plan.kind % 10) ? dispatch<true>(plan, p, stream, false) : dispatch<false>(plan, p, stream, false);
 }
 

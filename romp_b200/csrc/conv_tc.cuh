@@ -14,6 +14,7 @@ struct TcConvPlan {
   int smem_bytes = 0;
   void* d_wpack = nullptr;      // weights pre-arranged as the shared-memory image (bf16, swizzled)
   alignas(64) unsigned char tmap_in[128];   // CUtensorMap for the NHWC input tensor
+  alignas(64) unsigned char tmap_s2[4][128];  // stride-2: one map per input parity (ph,pw)
   std::string describe() const;
 };
 

@@ -1,0 +1,246 @@
+// tcgen05 implicit-GEMM for the 3x3 stride-2 convolutions (HRNet transitions, fuse down-sampling chains, stem
+// conv2, fused head-in conv; simple_romp/romp/model.py:201-218,275-285,341-343,449-457).
+//
+// A stride-2 3x3 conv on X[H,W,C] is a 2x2-tap stride-1 conv on the space-to-depth view X'[H/2,W/2,(ph,pw,C)]:
+// input row 2*oy+r-1 is (hh,ph) = (oy-1,1), (oy,0), (oy,1) for r = 0,1,2 (same for columns).  The NHWC tensor is
+// addressed by a 5-D TMA tensor map (dims: [pw*C+c], ww, ph, hh, n) so no data is rearranged in HBM.  Per
+// (tile, 64-channel chunk) the producer issues 4 TMA loads - one per input parity (ph,pw) - of
+// (17|16)x(9|8)-pixel sub-tiles; the 9 taps are shifted shared-memory descriptors into those 4 sub-tiles:
+//   tap (r,s) -> sub-tile (ph = r!=1, pw = s!=1), start row (r==2)*BW + (s==2), stride-byte-offset = BW rows.
+// Every input element is fetched once per tile (561 pixel rows instead of 9 x 128).  Everything else (resident
+// weights, TMEM accumulator ring, epilogue) is shared with conv_tc.cu.
+#include "tc_device.cuh"
+
+namespace b200romp {
+
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
+template <int CIN, int NT>
+struct S2Cfg {
+  static constexpr int CW = CIN < 64 ? CIN : 64;
+  static constexpr int KCH = CIN / CW;
+  static constexpr int ROWB = CW * 2;
+  static constexpr int LAYOUT = ROWB == 128 ? 2 : 4;
+  // sub-tile i = (ph ? 0 : 2) + (pw ? 0 : 1):  (1,1) 17x9, (1,0) 17x8, (0,1) 16x9, (0,0) 16x8
+  __host__ __device__ static constexpr int BH(int i) { return i < 2 ? 17 : 16; }
+  __host__ __device__ static constexpr int BW(int i) { return (i & 1) ? 8 : 9; }
+  __host__ __device__ static constexpr int SUB_BYTES(int i) { return (BH(i) * BW(i) * ROWB + 1023) / 1024 * 1024; }
+  __host__ __device__ static constexpr int SUB_OFF(int i) { return i == 0 ? 0 : SUB_OFF(i - 1) + SUB_BYTES(i - 1); }
+  static constexpr int STAGE_BYTES = SUB_OFF(3) + SUB_BYTES(3);
+  static constexpr int STAGE_PAYLOAD = (17 * 9 + 17 * 8 + 16 * 9 + 16 * 8) * ROWB;
+  static constexpr int BTILE = NT * ROWB;
+  static constexpr int B_BYTES = 9 * KCH * BTILE;
+  static constexpr int TMEM_COLS = kAccStages * NT <= 128 ? 128 : 256;
+  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+};
+
+struct S2Maps {
+  CUtensorMap m[4];
+};
+
+template <int CIN, int NT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_tc_s2_kernel(const __grid_constant__ S2Maps maps, const ConvParams p, const uint8_t* __restrict__ wpack, int tiles_x,
+                  int tiles_y, int num_tiles, int stages) {
+  using Cfg = S2Cfg<CIN, NT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sB = smem;
+  uint8_t* sA = smem + Cfg::B_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sA + (size_t)stages * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + stages;
+  uint64_t* b_full = empty + stages;
+  uint64_t* tmem_full = b_full + 1;
+  uint64_t* tmem_empty = tmem_full + kAccStages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + kAccStages);
+  float* s_bias = reinterpret_cast<float*>(tmem_ptr + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(b_full, 1);
+    for (int i = 0; i < kAccStages; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + NT) s_bias[threadIdx.x - 64] = p.bias[blockIdx.y * NT + threadIdx.x - 64];
+  if (warp == 1) tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int per_frame = tiles_x * tiles_y;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(b_full, Cfg::B_BYTES);
+      const uint8_t* wsrc = wpack + (size_t)blockIdx.y * Cfg::B_BYTES;
+      for (int i = 0; i < 9 * Cfg::KCH; ++i)
+        bulk_copy_g2s(sB + (size_t)i * Cfg::BTILE, wsrc + (size_t)i * Cfg::BTILE, Cfg::BTILE, b_full);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n = tile / per_frame, rem = tile % per_frame;
+        const int y0 = (rem / tiles_x) * 16, x0 = (rem % tiles_x) * 8;      // output coordinates
+        for (int c = 0; c < Cfg::KCH; ++c) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_PAYLOAD);
+          uint8_t* dst = sA + (size_t)stage * Cfg::STAGE_BYTES;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int ph = i < 2 ? 1 : 0, pw = (i & 1) ? 0 : 1;
+            tma_load_5d(dst + Cfg::SUB_OFF(i), &maps.m[i], &full[stage], pw * CIN + c * Cfg::CW, x0 - pw, ph, y0 - ph, n);
+          }
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(b_full, 0);
+      tc_fence_after();
+      const uint32_t b_base = smem_u32(sB);
+      int stage = 0, it = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & (kAccStages - 1);
+        mbar_wait(&tmem_empty[acc], ((it / kAccStages) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NT);
+        uint32_t accumulate = 0;
+        for (int c = 0; c < Cfg::KCH; ++c) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + (size_t)stage * Cfg::STAGE_BYTES);
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const int r = t / 3, s = t % 3;
+            const int sub = (r != 1 ? 0 : 2) + (s != 1 ? 0 : 1);
+            const int bw = Cfg::BW(sub);
+            const uint32_t a_tap = a_base + (uint32_t)(Cfg::SUB_OFF(sub) + ((r == 2 ? bw : 0) + (s == 2 ? 1 : 0)) * Cfg::ROWB);
+            const uint32_t b_tap = b_base + (uint32_t)((t * Cfg::KCH + c) * Cfg::BTILE);
+#pragma unroll
+            for (int k = 0; k < Cfg::CW / 16; ++k) {
+              const uint64_t adesc = make_smem_desc(a_tap + k * 32, bw * Cfg::ROWB, Cfg::LAYOUT);
+              const uint64_t bdesc = make_smem_desc(b_tap + k * 32, 8 * Cfg::ROWB, Cfg::LAYOUT);
+              umma_bf16(d_tmem, adesc, bdesc, Cfg::IDESC, accumulate);
+              accumulate = 1;
+            }
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else {
+    tc_epilogue_loop<NT>(p, tmem_base, tmem_full, tmem_empty, s_bias, tiles_x, per_frame, num_tiles);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+bool tc_s2_supported(const ConvParams& p) {
+  if (p.in_dtype != B200ROMP_BF16 || p.input_norm || p.out_nchw || p.pow_channel >= 0) return false;
+  if (p.cin != 32 && p.cin != 64 && p.cin != 128 && p.cin != 256) return false;
+  if (p.cin != p.in_C || p.in_c_off != 0) return false;        // (pw, c) must merge into one contiguous dim
+  if (p.cout % 32 != 0 || p.Hin % 2 != 0 || p.Win % 2 != 0) return false;
+  if (p.Hout % 16 != 0 || p.Wout % 8 != 0 || p.Hout * 2 != p.Hin || p.Wout * 2 != p.Win) return false;
+  if (p.out_C % 8 != 0 || p.out_c_off % 8 != 0) return false;
+  if (p.res != nullptr && (p.res_C % 8 != 0 || p.res_c_off % 8 != 0)) return false;
+  if ((reinterpret_cast<uintptr_t>(p.in) & 15) != 0) return false;
+  return true;
+}
+
+template <int CIN, int NT>
+static int s2_inst(const TcConvPlan& plan, const ConvParams& p, cudaStream_t stream, bool attr) {
+  auto kern = conv_tc_s2_kernel<CIN, NT>;
+  if (attr) {
+    B2R_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
+    return B200ROMP_OK;
+  }
+  S2Maps maps;
+  memcpy(&maps, plan.tmap_s2, sizeof(maps));
+  const int tiles_x = p.Wout / 8, tiles_y = p.Hout / 16;
+  const int num_tiles = tiles_x * tiles_y * p.B;
+  dim3 grid(std::min(plan.grid_x, num_tiles), plan.grid_y);
+  kern<<<grid, kTcThreads, plan.smem_bytes, stream>>>(maps, p, reinterpret_cast<const uint8_t*>(plan.d_wpack), tiles_x, tiles_y,
+                                                      num_tiles, plan.stages);
+  B2R_CUDA_OK(cudaGetLastError());
+  return B200ROMP_OK;
+}
+
+static int s2_dispatch(const TcConvPlan& plan, const ConvParams& p, cudaStream_t stream, bool attr) {
+#define B2R_S2(C, N) \
+  if (plan.cin == C && plan.nt == N) return s2_inst<C, N>(plan, p, stream, attr);
+  B2R_S2(32, 32) B2R_S2(32, 64) B2R_S2(64, 64) B2R_S2(128, 32) B2R_S2(256, 32)
+#undef B2R_S2
+  set_error("conv_tc_s2: no instantiation for cin%d nt%d", plan.cin, plan.nt);
+  return B200ROMP_EINVAL;
+}
+
+int tc_s2_prepare(const ConvParams& p, const float* w_oihw, int sm_count, TcConvPlan* plan, std::vector<void*>* allocs) {
+  PFN_encodeTiled encode = tc_get_encode();
+  if (!encode) {
+    set_error("conv_tc_s2: cuTensorMapEncodeTiled is unavailable");
+    return B200ROMP_ECUDA;
+  }
+  const int cw = p.cin < 64 ? p.cin : 64, kch = p.cin / cw, rowb = cw * 2;
+  auto sub_bytes = [&](int i) { return ((i < 2 ? 17 : 16) * ((i & 1) ? 8 : 9) * rowb + 1023) / 1024 * 1024; };
+  const int stage_bytes = sub_bytes(0) + sub_bytes(1) + sub_bytes(2) + sub_bytes(3);
+  const int budget = 227 * 1024 - 2048;
+  auto bbytes = [&](int n) { return 9 * kch * n * rowb; };
+  int nt = (p.cout % 64 == 0) ? 64 : 32;
+  if (nt == 64 && bbytes(64) + 2 * stage_bytes > budget && bbytes(32) + 2 * stage_bytes <= budget) nt = 32;
+  if (nt == 64 && bbytes(64) + stage_bytes > budget) nt = 32;
+  if (bbytes(nt) + stage_bytes > budget) {
+    set_error("conv_tc_s2: cin%d does not fit shared memory", p.cin);
+    return B200ROMP_EINVAL;
+  }
+  plan->stages = std::min(4, (budget - bbytes(nt)) / stage_bytes);
+  plan->kind = 32;
+  plan->cin = p.cin; plan->cout = p.cout; plan->nt = nt;
+  plan->grid_y = p.cout / nt;
+  plan->grid_x = std::max(1, sm_count / plan->grid_y);
+  plan->smem_bytes = bbytes(nt) + plan->stages * stage_bytes + 2048;
+  int rc = tc_pack_weights(w_oihw, p.cin, p.cout, 9, nt, &plan->d_wpack, allocs);
+  if (rc) return rc;
+  const cuuint64_t C = (cuuint64_t)p.in_C;
+  const cuuint64_t gdim[5] = {2 * C, (cuuint64_t)p.Win / 2, 2, (cuuint64_t)p.Hin / 2, (cuuint64_t)p.B};
+  const cuuint64_t gstr[4] = {2 * C * 2, (cuuint64_t)p.Win * C * 2, 2 * (cuuint64_t)p.Win * C * 2, (cuuint64_t)p.Hin * p.Win * C * 2};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; i < 4; ++i) {
+    const cuuint32_t box[5] = {(cuuint32_t)cw, (cuuint32_t)((i & 1) ? 8 : 9), 1, (cuuint32_t)(i < 2 ? 17 : 16), 1};
+    CUtensorMap tm;
+    CUresult cr = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(p.in), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+      set_error("conv_tc_s2: cuTensorMapEncodeTiled failed with %d", (int)cr);
+      return B200ROMP_ECUDA;
+    }
+    memcpy(plan->tmap_s2[i], &tm, sizeof(tm));
+  }
+  return s2_dispatch(*plan, p, nullptr, true);
+}
+
+int tc_s2_launch(const TcConvPlan& plan, const ConvParams& p, cudaStream_t stream) { return s2_dispatch(plan, p, stream, false); }
+
+}  // namespace b200romp
