@@ -27,6 +27,13 @@ CASES = [
     ("k3_c128_pt", 3, 128, 128, 16, 16, 2, 1, 2, 1, 1, 1),
     ("k3_c256", 3, 256, 256, 16, 16, 2, 1, 2, 1, 0, 1),
     ("k3_c256_n32", 3, 256, 32, 32, 32, 1, 1, 0, 1, 0, 1),
+    # stride-2 (13th field): H, W are INPUT sizes
+    ("s2_c64_single", 3, 64, 64, 32, 16, 1, 0, 0, 1, 0, 0, 2),
+    ("s2_c64_multi", 3, 64, 128, 64, 48, 2, 1, 2, 1, 0, 1, 2),
+    ("s2_c32_n32", 3, 32, 32, 64, 32, 2, 1, 1, 1, 0, 1, 2),
+    ("s2_c32_n192", 3, 32, 192, 32, 32, 2, 1, 0, 1, 0, 1, 2),
+    ("s2_c128_n256", 3, 128, 256, 32, 32, 2, 1, 2, 1, 0, 1, 2),
+    ("s2_c256_n64", 3, 256, 64, 32, 32, 2, 1, 0, 1, 0, 1, 2),
 ]
 PERF = [
     ("perf_k3_c64_64x64", 3, 64, 64, 64, 64, 64, 1, 2, 1, 0, 1),
@@ -35,7 +42,9 @@ PERF = [
     ("perf_k3_c256_16x16", 3, 256, 256, 16, 16, 64, 1, 2, 1, 0, 1),
     ("perf_k1_c64_n256_128", 1, 64, 256, 128, 128, 64, 1, 2, 1, 0, 1),
     ("perf_k3_c64_64x64_pt", 3, 64, 64, 64, 64, 64, 1, 2, 1, 1, 1),
-    ("perf_k3_c32_128x128_pt", 3, 32, 32, 128, 128, 64, 1, 2, 1, 1, 1),
+    ("perf_s2_c64_128to64", 3, 64, 64, 128, 128, 64, 1, 0, 1, 0, 1, 2),
+    ("perf_s2_c32_n64_128to64", 3, 32, 64, 128, 128, 64, 1, 0, 1, 0, 1, 2),
+    ("perf_k1_c256_n64_128", 1, 256, 64, 128, 128, 64, 1, 0, 1, 0, 1),
 ]
 
 
@@ -45,7 +54,8 @@ def run_case(case, perf):
     from romp_b200 import _lib
     from romp_b200._lib import BF16, F32
     from tests.gpu_util import conv2d, conv_ref
-    name, k, cin, cout, H, W, B, relu, res_mode, up, per_tap, out_bf16 = case
+    name, k, cin, cout, H, W, B, relu, res_mode, up, per_tap, out_bf16 = case[:12]
+    stride = case[12] if len(case) > 12 else 1
     os.environ["B200ROMP_TC_PER_TAP"] = "1" if per_tap else "0"
     rs = np.random.RandomState(len(name) * 131 + cin)
     x = torch.from_numpy(rs.normal(0, 1, (B, H, W, cin)).astype(np.float32)).cuda().bfloat16()
@@ -53,11 +63,11 @@ def run_case(case, perf):
     b = rs.normal(0, 0.5, cout).astype(np.float32)
     res = None
     if res_mode:
-        res = torch.from_numpy(rs.normal(0, 1, (B, H * up, W * up, cout)).astype(np.float32)).cuda()
+        res = torch.from_numpy(rs.normal(0, 1, (B, H // stride * up, W // stride * up, cout)).astype(np.float32)).cuda()
         if res_mode == 2:
             res = res.bfloat16()
     od = BF16 if out_bf16 else F32
-    got = conv2d(x, w, b, relu=bool(relu), res=res, up=up, out_dtype=od, engine=_lib.ENGINE_TCGEN05)
+    got = conv2d(x, w, b, stride=stride, relu=bool(relu), res=res, up=up, out_dtype=od, engine=_lib.ENGINE_TCGEN05)
     info = {"case": name}
     if perf:
         # time the library call with a prebuilt net to exclude packing: use the net API directly
@@ -72,9 +82,9 @@ def run_case(case, perf):
         t = tin
         resid = tin if (res_mode and cin == cout) else None
         for _ in range(4):
-            t = nb.conv(t, w, b, relu=bool(relu), res=resid if cin == cout else None)
+            t = nb.conv(t, w, b, stride=stride, relu=bool(relu), res=resid if (cin == cout and stride == 1) else None)
             resid = t if cin == cout else None
-            if cin != cout:
+            if cin != cout or stride != 1:
                 break
         nb.finalize(B)
         lib = nb.lib
@@ -93,9 +103,9 @@ def run_case(case, perf):
         st.synchronize()
         ms = e0.elapsed_time(e1) / iters
         # subtract nothing: the identity SIMT op is included; report both
-        flops = 2.0 * B * H * W * cout * cin * k * k * n_tc
+        flops = 2.0 * B * (H // stride) * (W // stride) * cout * cin * k * k * n_tc
         info.update(ms_per_run=ms, n_tc_ops=n_tc, tflops_incl_identity_op=flops / ms / 1e9, plan=nb.describe().splitlines()[1][:160])
-    ref = conv_ref(x.float(), w, b, relu=bool(relu), res=res, up=up)
+    ref = conv_ref(x.float(), w, b, stride=stride, relu=bool(relu), res=res, up=up)
     g = got.float().cpu()
     err = (g - ref).abs()
     tol = 0.02 + 0.02 * ref.abs() if out_bf16 else 2e-3 + 1e-3 * ref.abs()
@@ -110,6 +120,7 @@ def run_case(case, perf):
         bb = bad.nonzero()
         info["bad_examples"] = bb[:8].tolist()
         info["bad_pix_in_tile"] = sorted(set(((int(r[1]) % 16) * 8 + int(r[2]) % 8) for r in bb[:4000].tolist()))[:40]
+        info["bad_frames"] = sorted(set(int(r[0]) for r in bb[:4000].tolist()))
         info["bad_channels"] = sorted(set(int(r[3]) for r in bb[:4000].tolist()))[:40]
     print("PROBE " + json.dumps(info), flush=True)
 
