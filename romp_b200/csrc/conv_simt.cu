@@ -102,7 +102,99 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Stem: 3x3 stride-2 conv on the raw 3-channel frames (model.py:338-340,384-387).  HBM-bound in principle
+// (0.79 MB u8 in, 8.4 MB bf16 out per frame); K = 27 is too thin for a tensor-core tile, so: CTA = 8 x 32 output
+// pixels, one thread per pixel, all 64 channels in registers 16 at a time; the normalised input tile is staged in
+// shared memory with even/odd columns de-interleaved so that the stride-2 reads are bank-conflict free, and the
+// 27 x 64 weights are read as broadcast float4.  Output: 128 contiguous bytes per thread, 16-byte stores.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv_stem_kernel(const ConvParams p) {
+  constexpr int TW = 32, TH = 8, IH = 2 * TH + 1, HALF = TW + 1;
+  __shared__ float s_in[IH][2][HALF][3];
+  __shared__ __align__(16) float s_w[27][64];
+  __shared__ float s_b[64];
+  const int tid = threadIdx.x;
+  const int ox0 = blockIdx.x * TW, oy0 = blockIdx.y * TH, n = blockIdx.z;
+  const int iy0 = 2 * oy0 - 1, ix0 = 2 * ox0 - 1;
+  for (int idx = tid; idx < IH * (2 * HALF - 1) * 3; idx += 256) {
+    const int c = idx % 3, ix = (idx / 3) % (2 * HALF - 1), iy = idx / (3 * (2 * HALF - 1));
+    const int gy = iy0 + iy, gx = ix0 + ix;
+    float v = 0.f;
+    if (gy >= 0 && gy < p.Hin && gx >= 0 && gx < p.Win) {
+      const size_t gi = (((size_t)n * p.Hin + gy) * p.Win + gx) * p.in_C + p.in_c_off + c;
+      if (p.in_dtype == IN_F32) v = reinterpret_cast<const float*>(p.in)[gi];
+      else if (p.in_dtype == IN_BF16) v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.in)[gi]);
+      else v = (float)reinterpret_cast<const unsigned char*>(p.in)[gi];
+      if (p.input_norm) v = (v / 255.f) * 2.f - 1.f;
+    }
+    s_in[iy][ix & 1][ix >> 1][c] = v;
+  }
+  for (int idx = tid; idx < 27 * 64; idx += 256) {
+    const int co = idx & 63, k = idx >> 6;                 // k = tap*3 + ci, SIMT packing [tap][cin][coutPad]
+    s_w[k][co] = co < p.cout ? p.w[(size_t)k * p.coutPad + co] : 0.f;
+  }
+  if (tid < 64) s_b[tid] = p.bias[tid];
+  __syncthreads();
+  const int tx = tid & 31, ty = tid >> 5;
+  const int oy = oy0 + ty, ox = ox0 + tx;
+  float a[27];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) a[(ky * 3 + kx) * 3 + c] = s_in[2 * ty + ky][kx & 1][tx + (kx >> 1)][c];
+  if (oy >= p.Hout || ox >= p.Wout) return;
+  const size_t pix = ((size_t)n * p.Hout + oy) * p.Wout + ox;
+  for (int cg = 0; cg < p.cout; cg += 16) {
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = s_b[cg + j];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const float4 w4 = *reinterpret_cast<const float4*>(&s_w[k][cg + g * 4]);
+        acc[g * 4 + 0] = fmaf(a[k], w4.x, acc[g * 4 + 0]);
+        acc[g * 4 + 1] = fmaf(a[k], w4.y, acc[g * 4 + 1]);
+        acc[g * 4 + 2] = fmaf(a[k], w4.z, acc[g * 4 + 2]);
+        acc[g * 4 + 3] = fmaf(a[k], w4.w, acc[g * 4 + 3]);
+      }
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = fmaxf(acc[j], 0.f);
+    }
+    const size_t oi = pix * p.out_C + p.out_c_off + cg;
+    if (p.out_dtype == B200ROMP_BF16) {
+      uint4 pk[2];
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(pk);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) h[j] = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+      uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + oi);
+      o[0] = pk[0];
+      o[1] = pk[1];
+    } else {
+      float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + oi);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) o[g] = make_float4(acc[g * 4], acc[g * 4 + 1], acc[g * 4 + 2], acc[g * 4 + 3]);
+    }
+  }
+}
+
+static bool stem_eligible(const ConvParams& p, int ksize, int stride) {
+  return ksize == 3 && stride == 2 && p.cin == 3 && p.cout <= 64 && p.cout % 16 == 0 && !p.out_nchw && p.res == nullptr &&
+         p.up == 1 && p.pow_channel < 0 && p.out_C % 8 == 0 && p.out_c_off % 8 == 0;
+}
+
 int launch_conv_simt(const ConvParams& p, int ksize, int stride, cudaStream_t stream) {
+  if (stem_eligible(p, ksize, stride)) {
+    dim3 g((p.Wout + 31) / 32, (p.Hout + 7) / 8, p.B);
+    conv_stem_kernel<<<g, 256, 0, stream>>>(p);
+    B2R_CUDA_OK(cudaGetLastError());
+    return B200ROMP_OK;
+  }
   dim3 grid(((p.Hout + 7) / 8) * ((p.Wout + 7) / 8), (p.cout + 63) / 64, p.B);
   dim3 block(256);
   if (ksize == 3 && stride == 1) conv_simt_kernel<3, 1><<<grid, block, 0, stream>>>(p);

@@ -177,8 +177,8 @@ PFN_encodeTiled tc_get_encode() {
 }
 
 int tc_pack_weights(const float* w_oihw, int cin, int cout, int taps, int nt, void** d_out, std::vector<void*>* allocs) {
-  const int cw = cin < 64 ? cin : 64, kch = cin / cw, rowb = cw * 2, ntiles = cout / nt;
-  std::vector<__nv_bfloat16> img((size_t)ntiles * taps * kch * nt * cw);
+  const int cw = cin < 64 ? cin : 64, kch = cin / cw, rowb = cw * 2, ntiles = (cout + nt - 1) / nt;
+  std::vector<__nv_bfloat16> img((size_t)ntiles * taps * kch * nt * cw, __float2bfloat16_rn(0.f));
   for (int j = 0; j < ntiles; ++j)
     for (int t = 0; t < taps; ++t)
       for (int c = 0; c < kch; ++c) {
@@ -186,6 +186,7 @@ int tc_pack_weights(const float* w_oihw, int cin, int cout, int taps, int nt, vo
         for (int n = 0; n < nt; ++n)
           for (int k = 0; k < cw; ++k) {
             const int co = j * nt + n, ci = c * cw + k;
+            if (co >= cout) continue;                                     // zero rows pad cout up to a multiple of NT
             const float w = w_oihw[((size_t)co * cin + ci) * taps + t];
             const int chunk16 = k / 8;
             const int phase = rowb == 128 ? (n & 7) : ((n >> 1) & 3);     // Swizzle<3,4,3> / Swizzle<2,4,3>
@@ -213,11 +214,15 @@ std::string TcConvPlan::describe() const {
 bool tc_conv_supported(const ConvParams& p, int ksize, int stride) {
   if (stride == 2 && ksize == 3) return tc_s2_supported(p);
   if (stride != 1 || (ksize != 1 && ksize != 3)) return false;
-  if (p.in_dtype != B200ROMP_BF16 || p.input_norm || p.out_nchw || p.pow_channel >= 0) return false;
+  if (p.in_dtype != B200ROMP_BF16 || p.input_norm) return false;
   if (p.cin != 32 && p.cin != 64 && p.cin != 128 && p.cin != 256) return false;
-  if (p.cout % 32 != 0) return false;
   if (p.Hout % 16 != 0 || p.Wout % 8 != 0) return false;
   if (p.in_C % 8 != 0 || p.in_c_off % 8 != 0) return false;             // TMA: 16 B aligned base and strides
+  if (p.out_nchw) {                                                      // map outputs: any cout (padded to 32), scalar stores
+    if (p.out_dtype != B200ROMP_F32 || p.up != 1 || p.res != nullptr) return false;
+    return (reinterpret_cast<uintptr_t>(p.in) & 15) == 0;
+  }
+  if (p.pow_channel >= 0 || p.cout % 32 != 0) return false;
   if (p.out_C % 8 != 0 || p.out_c_off % 8 != 0) return false;           // 16 B vector epilogue
   if (p.res != nullptr && (p.res_C % 8 != 0 || p.res_c_off % 8 != 0)) return false;
   if ((reinterpret_cast<uintptr_t>(p.in) & 15) != 0) return false;
@@ -281,7 +286,7 @@ int tc_conv_prepare(const ConvParams& p, int ksize, int stride, const float* w_o
   stages = std::min(stages, per_tap ? 12 : 6);
   plan->kind = ksize * 10 + (per_tap ? 1 : 0);
   plan->cin = p.cin; plan->cout = p.cout; plan->nt = nt; plan->stages = stages;
-  plan->grid_y = p.cout / nt;
+  plan->grid_y = (p.cout + nt - 1) / nt;
   plan->grid_x = std::max(1, sm_count / plan->grid_y);
   plan->smem_bytes = bbytes(nt) + stages * stage_bytes + 1024 + 1024;
   int rcw = tc_pack_weights(w_oihw, p.cin, p.cout, taps, nt, &plan->d_wpack, allocs);

@@ -291,9 +291,16 @@ int b200romp_net_finalize(b200romp_net* net, int max_batch) {
                          (op.d.engine == B200ROMP_ENGINE_AUTO && ti.dtype == B200ROMP_BF16);
     if (want_tc) {
       ConvParams p;
-      // tensor pointers of internal tensors are final now; external ones are re-bound per run and are
-      // never routed to the tcgen05 engine (stem input / NCHW map outputs stay on the SIMT engine).
-      if (!ti.external && !to.external && fill_params(net, op, max_batch, &p) == B200ROMP_OK &&
+      // The TMA tensor map of the INPUT is baked now, so the input must be an internal tensor (final pointer);
+      // outputs / residuals are plain pointers read from ConvParams at launch and may be external (map outputs).
+      bool ext_out_unbound = false;
+      if (to.external && to.ptr == nullptr) {   // give fill_params a placeholder; the real pointer comes at run time
+        net->tensors[op.d.out].ptr = reinterpret_cast<void*>(16);
+        ext_out_unbound = true;
+      }
+      const bool params_ok = !ti.external && fill_params(net, op, max_batch, &p) == B200ROMP_OK;
+      if (ext_out_unbound) net->tensors[op.d.out].ptr = nullptr;
+      if (params_ok &&
           tc_conv_supported(p, op.d.ksize, op.d.stride)) {
         rc = tc_conv_prepare(p, op.d.ksize, op.d.stride, op.w_host.data(), net->sm_count, &op.tc, &net->device_allocs);
         if (rc == B200ROMP_OK) op.engine = B200ROMP_ENGINE_TCGEN05;

@@ -197,6 +197,21 @@ __device__ __forceinline__ void tc_epilogue_loop(const ConvParams& p, uint32_t t
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + s_bias[c0 + j];
+      if (p.out_nchw) {
+        // map outputs (ROMP head: [B,C,H,W] fp32, main.py:112-113): per channel a warp writes 4 x 32 B row segments
+        float* o = reinterpret_cast<float*>(p.out) + (((size_t)n * p.out_C + p.out_c_off + co0 + c0) * p.Hout + oy) * p.Wout + ox;
+        const size_t cstride = (size_t)p.Hout * p.Wout;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int c = co0 + c0 + j;
+          if (c < p.cout) {
+            float x = p.relu ? fmaxf(v[j], 0.f) : v[j];
+            if (c == p.pow_channel) x = powf(1.1f, x);
+            o[j * cstride] = x;
+          }
+        }
+        continue;
+      }
       for (int dy = 0; dy < up; ++dy) {
         for (int dx = 0; dx < up; ++dx) {
           const int fy = oy * up + dy, fx = ox * up + dx;

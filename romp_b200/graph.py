@@ -190,10 +190,10 @@ def build_romp(sd, device=0, precision="bf16", in_dtype=U8, max_batch=64, engine
         y = basic_block(y, q + "1.1.0.")
         w, b = fold_bn(sd, q + "2", None)
         if h == 3:      # cam maps -> params_maps[:, 0:3], cam scale 1.1**x (model.py:480, main.py:113)
-            nb.conv(y, w, b, out=params_maps, out_c_off=0, pow_channel=0, engine=_lib.ENGINE_SIMT)
+            nb.conv(y, w, b, out=params_maps, out_c_off=0, pow_channel=0)
         elif h == 1:    # params maps -> params_maps[:, 3:145]
-            nb.conv(y, w, b, out=params_maps, out_c_off=3, engine=_lib.ENGINE_SIMT)
+            nb.conv(y, w, b, out=params_maps, out_c_off=3)
         else:
-            nb.conv(y, w, b, out=center_maps, engine=_lib.ENGINE_SIMT)
+            nb.conv(y, w, b, out=center_maps)
     nb.finalize(max_batch)
     return nb, dict(frames=frames, center_maps=center_maps, params_maps=params_maps)

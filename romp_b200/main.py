@@ -161,17 +161,37 @@ class ROMP(torch.nn.Module):
         f32, i64 = torch.float32, torch.int64
         self.cap = cap
         z = lambda *shape, dtype=f32: torch.zeros(*shape, dtype=dtype, device=dev)
-        self.buf = dict(
-            center_maps=z(B, 1, 64, 64), params_maps=z(B, N_PARAMS, 64, 64),
-            count=z(1, dtype=torch.int32), batch_ids=z(cap, dtype=i64), flat_inds=z(cap, dtype=i64),
-            center_confs=z(cap, 1), params_pred=z(cap, N_PARAMS), cam=z(cap, 3), thetas=z(cap, 72), betas=z(cap, 10),
-            center_preds=z(cap, 2, dtype=i64),
-            parse_ws=torch.zeros(int(self.lib.b200romp_parse_workspace_bytes(B)), dtype=torch.uint8, device=dev),
-            cam_trans=z(cap, 3), pj2d_org=z(cap, 71, 2),
-        )
+        # shared scratch: only touched by kernels on self.stream, in order
+        self.shared = dict(
+            center_maps=z(B, 1, 64, 64), params_maps=z(B, N_PARAMS, 64, 64), flat_inds=z(cap, dtype=i64),
+            params_pred=z(cap, N_PARAMS),
+            parse_ws=torch.zeros(int(self.lib.b200romp_parse_workspace_bytes(B)), dtype=torch.uint8, device=dev))
         if self.calc_smpl:
-            self.buf.update(verts=z(cap, 6890, 3), joints=z(cap, 71, 3), smpl_ws=z(cap, self.smpl.ws_floats))
-        self.count_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            self.shared["smpl_ws"] = z(cap, self.smpl.ws_floats)
+        # two slots of per-person outputs (+ pinned host mirrors) so that batch i+1 can be computed while batch i
+        # is still being read back (forward_batches)
+        self.slots = []
+        for _ in range(2):
+            d = dict(count=z(1, dtype=torch.int32), batch_ids=z(cap, dtype=i64), center_confs=z(cap, 1), cam=z(cap, 3),
+                     thetas=z(cap, 72), betas=z(cap, 10), center_preds=z(cap, 2, dtype=i64), cam_trans=z(cap, 3),
+                     pj2d_org=z(cap, 71, 2))
+            if self.calc_smpl:
+                d.update(verts=z(cap, 6890, 3), joints=z(cap, 71, 3))
+            self.slots.append(dict(dev=d, host=None, count_host=torch.zeros(1, dtype=torch.int32).pin_memory(),
+                                   done=torch.cuda.Event(), frames={}, h2d=torch.cuda.Event()))
+        self._slot = 0
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.d2h_stream = torch.cuda.Stream(device=dev)
+
+    @property
+    def buf(self):
+        """device buffers of the slot used by the most recent batch (+ the shared maps)"""
+        return {**self.shared, **self.slots[self._slot]["dev"]}
+
+    def _host(self, slot):
+        if slot["host"] is None:      # pinned mirrors, allocated on first read-back
+            slot["host"] = {k: torch.zeros(v.shape, dtype=v.dtype).pin_memory() for k, v in slot["dev"].items() if k != "count"}
+        return slot["host"]
 
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -184,52 +204,62 @@ class ROMP(torch.nn.Module):
         nb, io = self._net(in_dtype)
         lib, sp = self.lib, C.c_void_p(self.stream.cuda_stream)
         _lib.check(lib.b200romp_net_bind(nb.net, io["frames"], _ptr(frames_dev)))
-        _lib.check(lib.b200romp_net_bind(nb.net, io["center_maps"], _ptr(self.buf["center_maps"])))
-        _lib.check(lib.b200romp_net_bind(nb.net, io["params_maps"], _ptr(self.buf["params_maps"])))
+        _lib.check(lib.b200romp_net_bind(nb.net, io["center_maps"], _ptr(self.shared["center_maps"])))
+        _lib.check(lib.b200romp_net_bind(nb.net, io["params_maps"], _ptr(self.shared["params_maps"])))
         _lib.check(lib.b200romp_net_run(nb.net, B, sp), "net_run")
-        return self.buf["center_maps"][:B], self.buf["params_maps"][:B]
+        return self.shared["center_maps"][:B], self.shared["params_maps"][:B]
 
     @torch.no_grad()
-    def run_post(self, B, offsets, center_override=None):
+    def run_post(self, B, offsets, center_override=None, slot=None):
         """Seams S2-S4 on the maps currently in the buffers; everything enqueued on self.stream, no host sync."""
-        b, lib, sp = self.buf, self.lib, C.c_void_p(self.stream.cuda_stream)
-        center = b["center_maps"] if center_override is None else center_override
-        _lib.check(lib.b200romp_parse(_ptr(center), _ptr(b["params_maps"]), B, 64, 10, float(self.settings.center_thresh),
-                                      self.cap, _ptr(b["count"]), _ptr(b["batch_ids"]), _ptr(b["flat_inds"]),
-                                      _ptr(b["center_confs"]), _ptr(b["params_pred"]), _ptr(b["cam"]), _ptr(b["thetas"]),
-                                      _ptr(b["betas"]), _ptr(b["center_preds"]), _ptr(b["parse_ws"]), sp), "parse")
+        sh, lib, sp = self.shared, self.lib, C.c_void_p(self.stream.cuda_stream)
+        b = (self.slots[self._slot] if slot is None else slot)["dev"]
+        center = sh["center_maps"] if center_override is None else center_override
+        _lib.check(lib.b200romp_parse(_ptr(center), _ptr(sh["params_maps"]), B, 64, 10, float(self.settings.center_thresh),
+                                      self.cap, _ptr(b["count"]), _ptr(b["batch_ids"]), _ptr(sh["flat_inds"]),
+                                      _ptr(b["center_confs"]), _ptr(sh["params_pred"]), _ptr(b["cam"]), _ptr(b["thetas"]),
+                                      _ptr(b["betas"]), _ptr(b["center_preds"]), _ptr(sh["parse_ws"]), sp), "parse")
         cap = B * MAX_PERSON
         off = (C.c_float * 6)(*[float(v) for v in offsets])
         if self.calc_smpl:
-            self.smpl.forward(b["betas"], b["thetas"], cap, b["count"], self.settings.root_align, b["smpl_ws"],
+            self.smpl.forward(b["betas"], b["thetas"], cap, b["count"], self.settings.root_align, sh["smpl_ws"],
                               b["verts"], b["joints"], self.stream.cuda_stream)
             _lib.check(lib.b200romp_project(_ptr(b["joints"]), None, _ptr(b["cam"]), cap, _ptr(b["count"]), off,
                                             _ptr(b["pj2d_org"]), None, None, _ptr(b["cam_trans"]), sp), "project")
-        else:
-            _lib.check(lib.b200romp_project(_ptr(b["joints"]) if "joints" in b else _ptr(b["cam"]), None, _ptr(b["cam"]),
-                                            cap, _ptr(b["count"]), off, None, None, _ptr(b["cam_trans"]), None, sp), "project")
+        else:   # without SMPL the reference keeps the weak-perspective translation of main.py:166
+            _lib.check(lib.b200romp_project(_ptr(b["cam"]), None, _ptr(b["cam"]), cap, _ptr(b["count"]), off, None, None,
+                                            _ptr(b["cam_trans"]), None, sp), "project")
 
-    def collect(self, to_numpy=True):
-        """The single host sync of a batch: person count, then D2H of the N valid rows (utils.py:32-41)."""
-        with torch.cuda.stream(self.stream):
-            self.count_host.copy_(self.buf["count"], non_blocking=True)
-        self.stream.synchronize()
-        n = int(self.count_host.item())
+    def _views(self, src, n):
+        out = {"cam": src["cam"][:n], "global_orient": src["thetas"][:n, :3], "body_pose": src["thetas"][:n, 3:],
+               "smpl_betas": src["betas"][:n], "smpl_thetas": src["thetas"][:n], "center_preds": src["center_preds"][:n],
+               "center_confs": src["center_confs"][:n], "cam_trans": src["cam_trans"][:n]}
+        if self.calc_smpl:
+            out.update(verts=src["verts"][:n], joints=src["joints"][:n], pj2d_org=src["pj2d_org"][:n])
+        out["pred_batch_ids"] = src["batch_ids"][:n]
+        return out
+
+    def collect(self, to_numpy=True, slot=None, stream=None):
+        """The single host sync of a batch: person count, then D2H of the N valid rows (utils.py:32-41) into pinned
+        host mirrors.  The returned numpy arrays are views of those mirrors: valid until the slot is reused, i.e.
+        until the second-next batch (copy them if they must live longer)."""
+        slot = self.slots[self._slot] if slot is None else slot
+        stream = self.stream if stream is None else stream
+        with torch.cuda.stream(stream):
+            slot["count_host"].copy_(slot["dev"]["count"], non_blocking=True)
+        stream.synchronize()
+        n = int(slot["count_host"].item())
         if n == 0:
             return None
-        b = self.buf
-        out = {
-            "cam": b["cam"][:n], "global_orient": b["thetas"][:n, :3], "body_pose": b["thetas"][:n, 3:],
-            "smpl_betas": b["betas"][:n], "smpl_thetas": b["thetas"][:n], "center_preds": b["center_preds"][:n],
-            "center_confs": b["center_confs"][:n], "cam_trans": b["cam_trans"][:n],
-        }
-        if self.calc_smpl:
-            out.update(verts=b["verts"][:n], joints=b["joints"][:n], pj2d_org=b["pj2d_org"][:n])
-        out["pred_batch_ids"] = b["batch_ids"][:n]
-        if to_numpy:
-            with torch.cuda.stream(self.stream):
-                out = {k: v.contiguous().cpu().numpy() for k, v in out.items()}
-        return out
+        if not to_numpy:
+            return self._views(slot["dev"], n)
+        host = self._host(slot)
+        with torch.cuda.stream(stream):
+            for k, v in slot["dev"].items():
+                if k != "count":
+                    host[k][:n].copy_(v[:n], non_blocking=True)
+        stream.synchronize()
+        return {k: v.numpy() for k, v in self._views(host, n).items()}
 
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -239,6 +269,7 @@ class ROMP(torch.nn.Module):
         if isinstance(frames, np.ndarray):
             frames = torch.from_numpy(frames)
         B = frames.shape[0]
+        self._slot ^= 1
         with torch.cuda.stream(self.stream):
             fd = frames.to(self.tdevice, non_blocking=True).contiguous()
             self.run_maps(fd)
@@ -246,6 +277,42 @@ class ROMP(torch.nn.Module):
         out = self.collect(to_numpy)
         del fd
         return out
+
+    @torch.no_grad()
+    def forward_batches(self, batches, offsets=None, center_override=None):
+        """Pipelined streaming over an iterable of host frame batches (video): yields one result dict (or None) per
+        batch, in order.  H2D of batch i+1 (copy stream) and D2H of batch i-1 (read-back stream) overlap the
+        kernels of batch i; the only host waits are on the person-count event of an already finished batch."""
+        off = offsets if offsets is not None else [0, 512, 0, 512, 512, 512]
+        pending = None
+        for frames in batches:
+            if isinstance(frames, np.ndarray):
+                frames = torch.from_numpy(frames)
+            B = frames.shape[0]
+            self._slot ^= 1
+            slot = self.slots[self._slot]
+            key = (frames.dtype, B)
+            if key not in slot["frames"]:
+                slot["frames"][key] = torch.empty((B, 512, 512, 3), dtype=frames.dtype, device=self.tdevice)
+            fd = slot["frames"][key]
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(slot["done"])          # the slot's previous kernels no longer read fd
+                fd.copy_(frames, non_blocking=True)
+                slot["h2d"].record(self.copy_stream)
+            with torch.cuda.stream(self.stream):
+                self.stream.wait_event(slot["h2d"])
+                self.run_maps(fd)
+                self.run_post(B, off, center_override, slot)
+                slot["done"].record(self.stream)
+            if pending is not None:
+                yield self._read_back(pending)
+            pending = slot
+        if pending is not None:
+            yield self._read_back(pending)
+
+    def _read_back(self, slot):
+        self.d2h_stream.wait_event(slot["done"])
+        return self.collect(True, slot, self.d2h_stream)
 
     @torch.no_grad()
     def forward(self, image, signal_ID=0, **kwargs):
@@ -256,10 +323,7 @@ class ROMP(torch.nn.Module):
             print("None person detected")                                       # post_parser.py:139
             return None
         out.pop("pred_batch_ids")
-        if not self.calc_smpl:
-            # without SMPL the reference keeps the weak-perspective translation of main.py:166
-            pass
-        return out
+        return {k: np.array(v) for k, v in out.items()}                          # own the memory like the reference
 
 
 default_settings = None   # the reference evaluates romp_settings([]) at import (main.py:62); we do not

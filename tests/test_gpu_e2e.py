@@ -111,3 +111,27 @@ def test_nobody_returns_none_and_single_image_forward(params):
     v, j = O.smpl_forward(params[1], ref["smpl_betas"], ref["smpl_thetas"])
     pr = O.project_outputs(j, None, ref["cam"], pad)
     assert np.abs(out["pj2d_org"] - pr["pj2d_org"].numpy()).max() < 0.5   # pixels in the 400x300 original image
+
+
+def test_forward_batches_pipeline_equals_forward_batch(params):
+    """The streaming API (H2D / kernels / D2H of neighbouring batches overlapped) returns, batch by batch, exactly
+    what the synchronous forward_batch returns."""
+    B = 3
+    m = make(params, "bf16", max_batch=B)
+    batches = [synth.synthetic_frames(B, seed=20 + i) for i in range(4)]
+    planted, _ = synth.plant_centers(B, seed=4)
+    planted = torch.from_numpy(planted).cuda()
+    ref = []
+    for fr in batches:
+        o = m.forward_batch(torch.from_numpy(fr), center_override=planted)
+        ref.append({k: np.array(v) for k, v in o.items()})
+    got = []
+    for o in m.forward_batches((torch.from_numpy(fr).pin_memory() for fr in batches), center_override=planted):
+        got.append({k: np.array(v) for k, v in o.items()})
+    assert len(got) == len(ref)
+    for a, b in zip(got, ref):
+        assert set(a) == set(b)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+    # batches really differ from each other (the pipeline did not return a stale slot)
+    assert not np.array_equal(got[0]["smpl_thetas"], got[1]["smpl_thetas"])
