@@ -165,6 +165,9 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         step_device()
         model.collect(to_numpy=False)
+    # warm the streaming path too (pinned read-back mirrors of both slots, per-slot frame buffers, CUDA graphs)
+    for _ in model.forward_batches((frames_host for _ in range(3)), center_override=planted):
+        pass
     # ---------------- device-resident timing (value) + net-only timing (roofline) --------------------------
     barrier()
     sampler = ClockSampler(local)
