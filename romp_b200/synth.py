@@ -232,3 +232,93 @@ def plant_centers(batch: int, seed: int = 0, kmin: int = 1, kmax: int = 10, size
         cur.sort(key=lambda t: -t[1])
         truth.append(cur)
     return maps, truth
+
+
+# --------------------------------------------------------------------------------------
+# BEV head parameters (simple_romp/bev/model.py:104-187): enumeration + synthetic values
+# --------------------------------------------------------------------------------------
+def bev_cam3dmap_anchor(fov=60, size=128):
+    """get_cam3dmap_anchor, bev/model.py:77-87: 64 strictly decreasing scale anchors."""
+    depth_level = np.array([1, 10, 20, 100], dtype=np.float32)
+    ranges = (np.array([2 / 64., 25 / 64., 3 / 64., 2 / 64.], dtype=np.float32) * size).astype(np.int32)
+    scale_level = 1 / np.tan(np.radians(fov / 2.)) / depth_level
+    out, cache = [], 8
+    for scale, r in zip(scale_level, ranges):
+        out.append(cache - np.arange(1, r + 1) / r * (cache - scale))
+        cache = scale
+    return np.concatenate(out).astype(np.float32)
+
+
+def bev_coordmap_3d(size=128):
+    """get_3Dcoord_maps_halfz, bev/model.py:9-17 -> [1,64,size,size,3] with last dim (Z=anchor, Y, X)."""
+    z = bev_cam3dmap_anchor(60, size)
+    r = np.arange(size, dtype=np.float32) / size * 2 - 1
+    D = len(z)
+    out = np.zeros((1, D, size, size, 3), np.float32)
+    out[..., 0] = z[None, :, None, None]
+    out[..., 1] = r[None, None, :, None]
+    out[..., 2] = r[None, None, None, :]
+    return out
+
+
+def bev_head_param_specs():
+    s = []
+
+    def conv(name, shape, bias=False):
+        s.append((name + ".weight", shape, "conv_w"))
+        if bias:
+            s.append((name + ".bias", (shape[0],), "conv_b", int(np.prod(shape[1:]))))
+
+    s.append(("coordmap_3d", (1, 64, 128, 128, 3), "coordmap"))
+    s.append(("position_embeddings.weight", (128, 128), "embed"))
+    for i, (o, c) in zip((0, 3, 6), ((512, 128), (512, 512), (143, 512))):
+        conv(f"transformer.{i}", (o, c), bias=True)
+    for head in ("det_head", "param_head"):
+        q = head + ".0.0."
+        conv(q + "conv1", (128, 32, 3, 3)); _bn(s, q + "bn1", 128)
+        conv(q + "conv2", (128, 128, 3, 3)); _bn(s, q + "bn2", 128)
+        conv(q + "downsample", (128, 32, 1, 1), bias=True)
+        if head == "det_head":
+            conv("det_head.1", (4, 128, 1, 1), bias=True)
+    conv("bv_pre_layers.0", (16, 32, 1, 1), bias=True); _bn(s, "bv_pre_layers.1", 16)
+    conv("bv_pre_layers.3", (16, 16, 3, 3), bias=True); _bn(s, "bv_pre_layers.4", 16)
+    conv("bv_pre_layers.6", (16, 16, 1, 1), bias=True); _bn(s, "bv_pre_layers.7", 16)
+    for i, (cin, cout) in enumerate(((2560, 512), (512, 512), (512, 128))):
+        q = f"bv_out_layers.{i}."
+        conv(q + "conv1", (cout, cin, 3)); _bn(s, q + "bn1", cout)
+        conv(q + "conv2", (cout, cout, 3)); _bn(s, q + "bn2", cout)
+    for name, c in (("center_map_refiner", 1), ("cam_map_refiner", 3)):
+        q = name + ".0."
+        conv(q + "conv1", (c, c, 3, 3, 3)); _bn(s, q + "bn1", c)
+        conv(q + "conv2", (c, c, 3, 3, 3)); _bn(s, q + "bn2", c)
+    return s
+
+
+def bev_state_dict(seed: int = 0, gain: float = 0.55):
+    """Synthetic BEVv1 state dict: ROMP's backbone keys + the BEV head keys (1871 entries like the reference)."""
+    sd = {k: v for k, v in romp_state_dict(seed, gain).items() if k.startswith("backbone.")}
+    rng = np.random.RandomState(seed + 31337)
+    for spec in bev_head_param_specs():
+        name, shape, kind = spec[0], spec[1], spec[2]
+        if kind == "coordmap":
+            sd[name] = bev_coordmap_3d(128)
+        elif kind == "embed":
+            v = rng.normal(0, 0.5, size=shape).astype(np.float32)
+            v[0] = 0.0                                   # nn.Embedding(padding_idx=0), bev/model.py:132
+            sd[name] = v
+        elif kind == "conv_w":
+            fan_in = int(np.prod(shape[1:]))
+            bound = gain * np.sqrt(3.0 / fan_in) * (2.0 if len(shape) == 5 else 1.0)
+            sd[name] = rng.uniform(-bound, bound, size=shape).astype(np.float32)
+        elif kind == "conv_b":
+            bound = 1.0 / np.sqrt(spec[3])
+            sd[name] = rng.uniform(-bound, bound, size=shape).astype(np.float32)
+        elif kind == "bn_w":
+            sd[name] = rng.uniform(0.5, 1.5, size=shape).astype(np.float32)
+        elif kind in ("bn_b", "bn_m"):
+            sd[name] = rng.normal(0.0, 0.1, size=shape).astype(np.float32)
+        elif kind == "bn_v":
+            sd[name] = rng.uniform(0.5, 1.5, size=shape).astype(np.float32)
+        elif kind == "bn_n":
+            sd[name] = np.array(1, dtype=np.int64)
+    return sd
