@@ -197,7 +197,10 @@ def bev_forward(sd, pack_a, pack_smil, frames_nhwc, thresh=0.08, nms_thresh=20, 
            "cam": pk["cam"], "smpl_thetas": pk["smpl_thetas"], "smpl_betas": pk["smpl_betas"], "cam_trans": cam_to_trans(pk["cam"])}
     verts, joints = smpla_forward(pack_a, pack_smil, res["smpl_betas"], res["smpl_thetas"])
     pj2d = perspective_project(joints, res["cam_trans"])
-    res.update(verts=verts, joints=joints, pj2d=pj2d, pj2d_org=R.to_org_image(pj2d, offsets))
+    # NB the reference maps pj2d to original-image pixels in place (bev/post_parser.py:129-136,150), so its later
+    # post-filters see pj2d == pj2d_org
+    res.update(verts=verts, joints=joints, pj2d_org=R.to_org_image(pj2d, offsets))
+    res["pj2d"] = res["pj2d_org"]
     keep = []
     for b in sorted(set(res["pred_batch_ids"].tolist())):       # the reference post-filters assume one frame
         idx = [i for i, v in enumerate(res["pred_batch_ids"].tolist()) if v == b]
