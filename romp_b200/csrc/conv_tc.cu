@@ -27,7 +27,7 @@
 
 namespace b200romp {
 
-template <int KS, int CIN, int NT, bool PER_TAP>
+template <int KS, int CIN, int NT, bool PER_TAP, int KSPLIT>
 struct TcCfg {
   static constexpr int TAPS = KS * KS;
   static constexpr int PAD = KS / 2;
@@ -42,15 +42,17 @@ struct TcCfg {
   static constexpr int STAGE_BYTES = (STAGE_PAYLOAD + 1023) / 1024 * 1024;
   static constexpr int BTILE = NT * ROWB;
   static constexpr int B_BYTES = TAPS * KCH * BTILE;
-  static constexpr int TMEM_COLS = kAccStages * NT <= 128 ? 128 : 256;
+  static constexpr int ACC = AccCfg<KSPLIT>::ACC;
+  static constexpr int TMEM_COLS = tc_tmem_cols(ACC * KSPLIT * NT);
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
 };
 
-template <int KS, int CIN, int NT, bool PER_TAP>
+template <int KS, int CIN, int NT, bool PER_TAP, int KSPLIT>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, const uint8_t* __restrict__ wpack,
                int tiles_x, int tiles_y, int num_tiles, int stages) {
-  using Cfg = TcCfg<KS, CIN, NT, PER_TAP>;
+  using Cfg = TcCfg<KS, CIN, NT, PER_TAP, KSPLIT>;
+  constexpr int kAccStages = Cfg::ACC;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sB = smem;
@@ -121,8 +123,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, con
         const int acc = it & (kAccStages - 1);
         mbar_wait(&tmem_empty[acc], ((it / kAccStages) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NT);
-        uint32_t accumulate = 0;
+        const uint32_t d_tile = tmem_base + (uint32_t)(acc * KSPLIT * NT);
+        int mma_i = 0;
         for (int c = 0; c < Cfg::KCH; ++c) {
           for (int l = 0; l < Cfg::LOADS_PER_CHUNK; ++l) {
             mbar_wait(&full[stage], phase);
@@ -137,8 +139,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, con
               for (int k = 0; k < Cfg::CW / 16; ++k) {
                 const uint64_t adesc = make_smem_desc(a_tap + k * 32, Cfg::HW_ * Cfg::ROWB, Cfg::LAYOUT);
                 const uint64_t bdesc = make_smem_desc(b_tap + k * 32, 8 * Cfg::ROWB, Cfg::LAYOUT);
-                umma_bf16(d_tmem, adesc, bdesc, Cfg::IDESC, accumulate);
-                accumulate = 1;
+                umma_bf16(d_tile + (uint32_t)((mma_i % KSPLIT) * NT), adesc, bdesc, Cfg::IDESC, mma_i >= KSPLIT ? 1u : 0u);
+                ++mma_i;
               }
             }
             umma_commit(&empty[stage]);          // smem stage reusable once these MMAs retire
@@ -149,7 +151,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, con
       }
     }
   } else {
-    tc_epilogue_loop<NT>(p, tmem_base, tmem_full, tmem_empty, s_bias, tiles_x, per_frame, num_tiles);
+    tc_epilogue_loop<NT, KSPLIT>(p, tmem_base, tmem_full, tmem_empty, s_bias, tiles_x, per_frame, num_tiles);
   }
   tc_fence_before();
   __syncthreads();
@@ -200,11 +202,6 @@ int tc_pack_weights(const float* w_oihw, int cin, int cout, int taps, int nt, vo
   return B200ROMP_OK;
 }
 
-static bool tc_per_tap() {
-  const char* e = getenv("B200ROMP_TC_PER_TAP");
-  return e && e[0] == '1';
-}
-
 std::string TcConvPlan::describe() const {
   char buf[96];
   snprintf(buf, sizeof(buf), " [tc k%d v%d nt%d grid %dx%d smem %d stages %d]", kind / 10, kind % 10, nt, grid_x, grid_y, smem_bytes, stages);
@@ -229,9 +226,9 @@ bool tc_conv_supported(const ConvParams& p, int ksize, int stride) {
   return true;
 }
 
-template <int KS, int CIN, int NT, bool PER_TAP>
+template <int KS, int CIN, int NT, bool PER_TAP, int KSPLIT>
 static int launch_inst(const TcConvPlan& plan, const ConvParams& p, cudaStream_t stream, bool set_attr_only) {
-  auto kern = conv_tc_kernel<KS, CIN, NT, PER_TAP>;
+  auto kern = conv_tc_kernel<KS, CIN, NT, PER_TAP, KSPLIT>;
   if (set_attr_only) {
     B2R_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
     return B200ROMP_OK;
@@ -250,8 +247,11 @@ static int launch_inst(const TcConvPlan& plan, const ConvParams& p, cudaStream_t
 template <bool PER_TAP>
 static int dispatch(const TcConvPlan& plan, const ConvParams& p, cudaStream_t stream, bool attr) {
   const int ks = plan.kind / 10;
-#define B2R_CASE(K, C, N) \
-  if (ks == K && plan.cin == C && plan.nt == N) return launch_inst<K, C, N, PER_TAP>(plan, p, stream, attr);
+#define B2R_CASE(K, C, N)                                                                            \
+  if (ks == K && plan.cin == C && plan.nt == N) {                                                   \
+    if (plan.ksplit == 1) return launch_inst<K, C, N, PER_TAP, 1>(plan, p, stream, attr);            \
+    return launch_inst<K, C, N, PER_TAP, tc_ksplit(K * K * (C / 16), N)>(plan, p, stream, attr);      \
+  }
   B2R_CASE(3, 32, 32) B2R_CASE(3, 64, 64) B2R_CASE(3, 128, 64) B2R_CASE(3, 256, 32)
   B2R_CASE(1, 64, 32) B2R_CASE(1, 64, 64) B2R_CASE(1, 128, 32) B2R_CASE(1, 128, 64) B2R_CASE(1, 256, 32)
   B2R_CASE(1, 256, 64)
@@ -268,7 +268,8 @@ int tc_conv_prepare(const ConvParams& p, int ksize, int stride, const float* w_o
     set_error("conv_tc: cuTensorMapEncodeTiled is unavailable");
     return B200ROMP_ECUDA;
   }
-  const bool per_tap = tc_per_tap();
+  const bool per_tap = false;   // the per-tap TMA variant (PER_TAP=true) was only the bring-up fallback
+  { const char* e = getenv("B200ROMP_TC_KSPLIT"); plan->ksplit = (e && e[0] == '1') ? 1 : 0; }
   const int taps = ksize * ksize;
   const int cw = p.cin < 64 ? p.cin : 64, kch = p.cin / cw, rowb = cw * 2;
   // N tile: weights must stay resident next to >= 2 pipeline stages
@@ -306,12 +307,12 @@ int tc_conv_prepare(const ConvParams& p, int ksize, int stride, const float* w_o
     return B200ROMP_ECUDA;
   }
   memcpy(plan->tmap_in, &tm, sizeof(tm));
-  return per_tap ? dispatch<true>(*plan, p, nullptr, true) : dispatch<false>(*plan, p, nullptr, true);
+  return dispatch<false>(*plan, p, nullptr, true);
 }
 
 int tc_conv_launch(const TcConvPlan& plan, const ConvParams& p, cudaStream_t stream) {
   if (plan.kind % 10 == 2) return tc_s2_launch(plan, p, stream);
-  return (plan.kind % 10) ? dispatch<true>(plan, p, stream, false) : dispatch<false>(plan, p, stream, false);
+  return dispatch<false>(plan, p, stream, false);
 }
 
 }  // namespace b200romp

@@ -11,6 +11,7 @@ struct TcConvPlan {
   int kind = 0;                 // kernel family, 0 = none
   int cin = 0, cout = 0, nt = 0;  // channels, output channels per CTA
   int grid_x = 0, grid_y = 0, stages = 0;
+  int ksplit = 0;               // 1 = single accumulator per tile (bring-up mode), 0 = K-split accumulators
   int smem_bytes = 0;
   void* d_wpack = nullptr;      // weights pre-arranged as the shared-memory image (bf16, swizzled)
   alignas(64) unsigned char tmap_in[128];   // CUtensorMap for the NHWC input tensor

@@ -21,7 +21,7 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, u
       : "memory");
 }
 
-template <int CIN, int NT>
+template <int CIN, int NT, int KSPLIT>
 struct S2Cfg {
   static constexpr int CW = CIN < 64 ? CIN : 64;
   static constexpr int KCH = CIN / CW;
@@ -36,7 +36,8 @@ struct S2Cfg {
   static constexpr int STAGE_PAYLOAD = (17 * 9 + 17 * 8 + 16 * 9 + 16 * 8) * ROWB;
   static constexpr int BTILE = NT * ROWB;
   static constexpr int B_BYTES = 9 * KCH * BTILE;
-  static constexpr int TMEM_COLS = kAccStages * NT <= 128 ? 128 : 256;
+  static constexpr int ACC = AccCfg<KSPLIT>::ACC;
+  static constexpr int TMEM_COLS = tc_tmem_cols(ACC * KSPLIT * NT);
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
 };
 
@@ -44,11 +45,12 @@ struct S2Maps {
   CUtensorMap m[4];
 };
 
-template <int CIN, int NT>
+template <int CIN, int NT, int KSPLIT>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_s2_kernel(const __grid_constant__ S2Maps maps, const ConvParams p, const uint8_t* __restrict__ wpack, int tiles_x,
                   int tiles_y, int num_tiles, int stages) {
-  using Cfg = S2Cfg<CIN, NT>;
+  using Cfg = S2Cfg<CIN, NT, KSPLIT>;
+  constexpr int kAccStages = Cfg::ACC;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sB = smem;
@@ -117,8 +119,8 @@ conv_tc_s2_kernel(const __grid_constant__ S2Maps maps, const ConvParams p, const
         const int acc = it & (kAccStages - 1);
         mbar_wait(&tmem_empty[acc], ((it / kAccStages) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NT);
-        uint32_t accumulate = 0;
+        const uint32_t d_tile = tmem_base + (uint32_t)(acc * KSPLIT * NT);
+        int mma_i = 0;
         for (int c = 0; c < Cfg::KCH; ++c) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
@@ -134,8 +136,8 @@ conv_tc_s2_kernel(const __grid_constant__ S2Maps maps, const ConvParams p, const
             for (int k = 0; k < Cfg::CW / 16; ++k) {
               const uint64_t adesc = make_smem_desc(a_tap + k * 32, bw * Cfg::ROWB, Cfg::LAYOUT);
               const uint64_t bdesc = make_smem_desc(b_tap + k * 32, 8 * Cfg::ROWB, Cfg::LAYOUT);
-              umma_bf16(d_tmem, adesc, bdesc, Cfg::IDESC, accumulate);
-              accumulate = 1;
+              umma_bf16(d_tile + (uint32_t)((mma_i % KSPLIT) * NT), adesc, bdesc, Cfg::IDESC, mma_i >= KSPLIT ? 1u : 0u);
+              ++mma_i;
             }
           }
           umma_commit(&empty[stage]);
@@ -145,7 +147,7 @@ conv_tc_s2_kernel(const __grid_constant__ S2Maps maps, const ConvParams p, const
       }
     }
   } else {
-    tc_epilogue_loop<NT>(p, tmem_base, tmem_full, tmem_empty, s_bias, tiles_x, per_frame, num_tiles);
+    tc_epilogue_loop<NT, KSPLIT>(p, tmem_base, tmem_full, tmem_empty, s_bias, tiles_x, per_frame, num_tiles);
   }
   tc_fence_before();
   __syncthreads();
@@ -169,9 +171,9 @@ bool tc_s2_supported(const ConvParams& p) {
   return true;
 }
 
-template <int CIN, int NT>
+template <int CIN, int NT, int KSPLIT>
 static int s2_inst(const TcConvPlan& plan, const ConvParams& p, cudaStream_t stream, bool attr) {
-  auto kern = conv_tc_s2_kernel<CIN, NT>;
+  auto kern = conv_tc_s2_kernel<CIN, NT, KSPLIT>;
   if (attr) {
     B2R_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
     return B200ROMP_OK;
@@ -188,8 +190,11 @@ static int s2_inst(const TcConvPlan& plan, const ConvParams& p, cudaStream_t str
 }
 
 static int s2_dispatch(const TcConvPlan& plan, const ConvParams& p, cudaStream_t stream, bool attr) {
-#define B2R_S2(C, N) \
-  if (plan.cin == C && plan.nt == N) return s2_inst<C, N>(plan, p, stream, attr);
+#define B2R_S2(C, N)                                                                 \
+  if (plan.cin == C && plan.nt == N) {                                             \
+    if (plan.ksplit == 1) return s2_inst<C, N, 1>(plan, p, stream, attr);          \
+    return s2_inst<C, N, tc_ksplit(9 * (C / 16), N)>(plan, p, stream, attr);       \
+  }
   B2R_S2(32, 32) B2R_S2(32, 64) B2R_S2(64, 64) B2R_S2(128, 32) B2R_S2(256, 32)
 #undef B2R_S2
   set_error("conv_tc_s2: no instantiation for cin%d nt%d", plan.cin, plan.nt);
@@ -216,6 +221,7 @@ int tc_s2_prepare(const ConvParams& p, const float* w_oihw, int sm_count, TcConv
   }
   plan->stages = std::min(4, (budget - bbytes(nt)) / stage_bytes);
   plan->kind = 32;
+  { const char* e = getenv("B200ROMP_TC_KSPLIT"); plan->ksplit = (e && e[0] == '1') ? 1 : 0; }
   plan->cin = p.cin; plan->cout = p.cout; plan->nt = nt;
   plan->grid_y = p.cout / nt;
   plan->grid_x = std::max(1, sm_count / plan->grid_y);

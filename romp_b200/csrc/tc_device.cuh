@@ -164,13 +164,24 @@ __device__ __forceinline__ void tc_store32(const ConvParams& p, size_t pix, size
   }
 }
 
-constexpr int kAccStages = 4;        // TMEM accumulator ring (4 x NT columns <= 256)
+// TMEM accumulator organisation.  A tcgen05.mma that accumulates into the SAME TMEM tile as its predecessor cannot
+// overlap with it (measured: ~120 clk per dependent MMA whatever N is), so the K loop of one tile is spread
+// round-robin over KSPLIT independent accumulators that the epilogue adds up; ACC tiles are in flight.
+template <int KSPLIT>
+struct AccCfg {
+  static constexpr int ACC = KSPLIT == 1 ? 4 : 2;
+};
+// accumulators per tile: as many as TMEM allows (2 tiles x KSPLIT x NT <= 512 columns), never more than the MMAs of a tile
+__host__ __device__ constexpr int tc_ksplit(int mmas_per_tile, int nt) {
+  return (nt == 32 ? 8 : 4) < mmas_per_tile ? (nt == 32 ? 8 : 4) : (mmas_per_tile >= 4 ? 4 : (mmas_per_tile >= 2 ? 2 : 1));
+}
+__host__ __device__ constexpr int tc_tmem_cols(int cols) { return cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512; }
 constexpr int kEpiWarps = 8;         // two groups of 4 warps, alternating tiles
 constexpr int kTcThreads = 64 + kEpiWarps * 32;
 
 // Epilogue of a persistent tile loop: 2 groups x 4 warps (warps 2..9), group g takes the CTA's tiles g, g+2, ...
 // Each warp owns the TMEM lane quarter (warp id mod 4); thread = one pixel of the 16x8 tile.
-template <int NT>
+template <int NT, int KSPLIT>
 __device__ __forceinline__ void tc_epilogue_loop(const ConvParams& p, uint32_t tmem_base, uint64_t* tmem_full,
                                                  uint64_t* tmem_empty, const float* s_bias, int tiles_x, int per_frame,
                                                  int num_tiles) {
@@ -183,20 +194,26 @@ __device__ __forceinline__ void tc_epilogue_loop(const ConvParams& p, uint32_t t
   const int Hf = p.Hout * up, Wf = p.Wout * up;
   int it = group;
   for (int tile = blockIdx.x + group * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, it += 2) {
-    const int acc = it & (kAccStages - 1);
+    constexpr int ACC = AccCfg<KSPLIT>::ACC;
+    const int acc = it & (ACC - 1);
     const int n = tile / per_frame, rem = tile % per_frame;
     const int oy = (rem / tiles_x) * 16 + (m >> 3), ox = (rem % tiles_x) * 8 + (m & 7);
-    mbar_wait(&tmem_full[acc], (it / kAccStages) & 1);
+    mbar_wait(&tmem_full[acc], (it / ACC) & 1);
     tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT);
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * KSPLIT * NT);
 #pragma unroll
     for (int c0 = 0; c0 < NT; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld32(taddr + c0, r);
-      tmem_ld_wait();
       float v[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + s_bias[c0 + j];
+      for (int j = 0; j < 32; ++j) v[j] = s_bias[c0 + j];
+#pragma unroll
+      for (int ks = 0; ks < KSPLIT; ++ks) {      // partial sums of the K-split accumulators
+        uint32_t r[32];
+        tmem_ld32(taddr + ks * NT + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(r[j]);
+      }
       if (p.out_nchw) {
         // map outputs (ROMP head: [B,C,H,W] fp32, main.py:112-113): per channel a warp writes 4 x 32 B row segments
         float* o = reinterpret_cast<float*>(p.out) + (((size_t)n * p.out_C + p.out_c_off + co0 + c0) * p.Hout + oy) * p.Wout + ox;
