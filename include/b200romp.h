@@ -148,6 +148,56 @@ int b200romp_project(const float* joints /*[n,71,3]*/, const float* verts /*[n,6
                      float* verts_camed_org /*[n,6890,3] or NULL*/, float* cam_trans_weak /*[n,3] or NULL*/,
                      float* cam_trans_lsq /*[n,3] or NULL*/, b200romp_stream stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * BEV variant (simple_romp/bev): the stages of BEVv1.forward (bev/model.py:232-250) and of
+ * BEV.process_normal_image (bev/main.py:158-181) that are not 2-D/1-D convolutions.  The convolutions
+ * (backbone, det_head, param_head, bv_pre_layers, bv_out_layers' Conv1d as ksize code 13 = 1x3) run on
+ * b200romp_net graphs.  All maps are 128x128, 64 depth levels.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct b200romp_bev b200romp_bev;
+typedef struct b200romp_bev_weights {   /* host fp32 arrays */
+  const float* center_ref;  /* [56]  center_map_refiner, BatchNorm3d folded: w1[27], b1, w2[27], b2   (bev/model.py:185)  */
+  const float* cam_ref;     /* [168] cam_map_refiner: w1[3][3][27], b1[3], w2[3][3][27], b2[3]          (bev/model.py:186)  */
+  const float* coordmap;    /* [64,128,128,3] coordmap_3d buffer                                       (bev/model.py:128)  */
+  const float* anchors;     /* [64]  cam3dmap_anchor                                                   (bev/model.py:77-87) */
+  const float* embed;       /* [128,128] position_embeddings.weight                                    (bev/model.py:132)  */
+  const float *w0, *b0, *w1, *b1, *w2, *b2;   /* transformer.{0,3,6}: [512,128],[512],[512,512],[512],[143,512],[143]   */
+} b200romp_bev_weights;
+b200romp_bev* b200romp_bev_create(int device, const b200romp_bev_weights* w);
+void b200romp_bev_destroy(b200romp_bev* bev);
+/* summon_feats = cat([center_fv, cam_offset, img_feats],1).view(B,2560,128) (bev/model.py:190), stored as the NHWC
+ * "image" [B,1,128(w),2560] consumed by the Conv1d graph.  maps_fv [B,4,128,128] fp32 NCHW, img_feats [B,128,128,16]. */
+int b200romp_bev_bv_input(const float* maps_fv, const void* img_feats, int feats_dtype, int batch, void* out, int out_dtype,
+                          b200romp_stream stream);
+/* center_maps_3d [B,64,128,128] = refiner(center_fv (x) center_bv) (bev/model.py:195-196,206); bv_out = output of
+ * bv_out_layers as NHWC [B,1,128(w),128(ch)] (ch < 64: center_maps_bv, >= 64: cam_maps_offset_bv); tmp: same size scratch. */
+int b200romp_bev_center3d(b200romp_bev* bev, const float* maps_fv, const void* bv_out, int bv_dtype, int batch, float* tmp,
+                          float* center3d, b200romp_stream stream);
+/* CenterMap3D.parse_3dcentermap (bev/post_parser.py:44-66): 5x5x5 NMS, top-64 per frame, > thresh.  Order: frame asc,
+ * score desc (ties: voxel index asc).  Exact as long as a frame has <= 4096 local maxima above thresh. */
+long long b200romp_bev_parse_workspace_bytes(int batch);
+int b200romp_bev_parse3d(const float* center3d, int batch, float thresh, int capacity, int* d_count, long long* batch_ids,
+                         long long* czyx /*[cap,3]*/, float* conf, void* workspace, b200romp_stream stream);
+/* cams = cam_maps_3d[b,:,z,y,x] (refiner evaluated lazily at the detections), mesh_parameter_regression
+ * (bev/model.py:225-230) -> params_pred [cap,146], cam_czyx [cap,3]; then pack_params_dict / denormalize_cam_params_to_trans
+ * (bev/post_parser.py:240-253,114-128) -> cam [cap,3], thetas [cap,72], betas [cap,11], cam_trans [cap,3].
+ * fv_feats = param_head output NHWC [B,128,128,128]. */
+int b200romp_bev_regress(b200romp_bev* bev, const float* maps_fv, const void* bv_out, int bv_dtype, const void* fv_feats,
+                         int fv_dtype, int capacity, const int* d_count, const long long* batch_ids, const long long* czyx,
+                         float* params_pred, long long* cam_czyx, float* cam, float* thetas, float* betas, float* cam_trans,
+                         b200romp_stream stream);
+/* After SMPL-A (into verts/joints) and SMIL (into verts_smil/joints_smil, may be NULL): merge babies (betas[:,10] > 0.8,
+ * bev/post_parser.py:255-278), perspective projection to original-image pixels (:68-107,129-152), then per frame
+ * suppressing_redundant_prediction_via_projection and remove_outlier (:167-222).  keep[cap] flags, sel[cap] = indices of
+ * the survivors in order, *d_count_out = their number. */
+int b200romp_bev_post(const float* betas, const float* verts_smil, const float* joints_smil, float* verts, float* joints,
+                      const float* cam, const float* cam_trans, const long long* batch_ids, int batch, int capacity,
+                      const int* d_count, const float* offsets6, float nms_thresh, float rel_scale_thresh, float img_max_side,
+                      float* pj2d_org, int* keep, int* sel, int* d_count_out, b200romp_stream stream);
+/* dst[i] = src[sel[i]] for i < *d_count; rows of row_bytes (multiple of 4) bytes. */
+int b200romp_gather_rows(const void* src, int row_bytes, const int* sel, const int* d_count, int capacity, void* dst,
+                         b200romp_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

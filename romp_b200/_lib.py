@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "lib", "libb200romp.so")
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["net.cu", "conv_simt.cu", "conv_tc.cu", "conv_tc_s2.cu", "parse.cu", "smpl.cu", "project.cu"]
+SOURCES = ["net.cu", "conv_simt.cu", "conv_tc.cu", "conv_tc_s2.cu", "parse.cu", "smpl.cu", "project.cu", "bev.cu"]
 
 F32, BF16, U8 = 0, 1, 2
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
@@ -24,6 +24,11 @@ class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "in_", "in_c_off", "out", "out_c_off", "res", "res_c_off", "res_broadcast", "cin", "cout",
         "ksize", "stride", "relu", "upsample", "input_norm", "pow_channel", "engine")]
+
+
+class BevWeights(C.Structure):
+    _fields_ = [(n, C.POINTER(C.c_float)) for n in (
+        "center_ref", "cam_ref", "coordmap", "anchors", "embed", "w0", "b0", "w1", "b1", "w2", "b2")]
 
 
 def nvcc_command(out_path=LIB_PATH):
@@ -96,6 +101,15 @@ def load():
     _sig(lib.b200romp_smpl_workspace_floats, i32)
     _sig(lib.b200romp_smpl_forward, i32, vp, vp, i32, vp, i32, vp, i32, vp, vp, vp, vp)
     _sig(lib.b200romp_project, i32, vp, vp, vp, i32, vp, fp, vp, vp, vp, vp, vp)
+    _sig(lib.b200romp_bev_create, vp, i32, C.POINTER(BevWeights))
+    _sig(lib.b200romp_bev_destroy, None, vp)
+    _sig(lib.b200romp_bev_bv_input, i32, vp, vp, i32, i32, vp, i32, vp)
+    _sig(lib.b200romp_bev_center3d, i32, vp, vp, vp, i32, i32, vp, vp, vp)
+    _sig(lib.b200romp_bev_parse_workspace_bytes, i64, i32)
+    _sig(lib.b200romp_bev_parse3d, i32, vp, i32, f32, i32, vp, vp, vp, vp, vp, vp)
+    _sig(lib.b200romp_bev_regress, i32, vp, vp, vp, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp)
+    _sig(lib.b200romp_bev_post, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, fp, f32, f32, f32, vp, vp, vp, vp, vp)
+    _sig(lib.b200romp_gather_rows, i32, vp, i32, vp, vp, i32, vp, vp)
     if lib.b200romp_version() != 100:
         raise RuntimeError("libb200romp.so version mismatch - rebuild")
     _lib = lib
@@ -116,4 +130,7 @@ EXPORTS = [
     "b200romp_net_describe", "b200romp_net_num_launches", "b200romp_net_workspace_bytes", "b200romp_conv2d",
     "b200romp_parse", "b200romp_parse_workspace_bytes", "b200romp_smpl_create", "b200romp_smpl_destroy",
     "b200romp_smpl_workspace_floats", "b200romp_smpl_forward", "b200romp_project",
+    "b200romp_bev_create", "b200romp_bev_destroy", "b200romp_bev_bv_input", "b200romp_bev_center3d",
+    "b200romp_bev_parse_workspace_bytes", "b200romp_bev_parse3d", "b200romp_bev_regress", "b200romp_bev_post",
+    "b200romp_gather_rows",
 ]

@@ -18,14 +18,14 @@ namespace b200romp {
 
 enum { IN_F32 = 0, IN_BF16 = 1, IN_U8 = 2 };
 
-template <int KS, int STRIDE>
+template <int KH, int KW, int STRIDE>
 __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvParams p) {
   constexpr int TS = 8;
-  constexpr int IT = (TS - 1) * STRIDE + KS;
+  constexpr int ITH = (TS - 1) * STRIDE + KH, ITW = (TS - 1) * STRIDE + KW;
   constexpr int KC = 8;
-  constexpr int PAD = KS / 2;
-  __shared__ float s_in[IT * IT][KC + 1];
-  __shared__ __align__(16) float s_w[KS * KS][KC][64];
+  constexpr int PADH = KH / 2, PADW = KW / 2;
+  __shared__ float s_in[ITH * ITW][KC + 1];
+  __shared__ __align__(16) float s_w[KH * KW][KC][64];
 
   const int tid = threadIdx.x;
   const int tilesX = (p.Wout + TS - 1) / TS;
@@ -41,11 +41,11 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvParams p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  const int iy0 = oy0 * STRIDE - PAD, ix0 = ox0 * STRIDE - PAD;
+  const int iy0 = oy0 * STRIDE - PADH, ix0 = ox0 * STRIDE - PADW;
   for (int c0 = 0; c0 < p.cin; c0 += KC) {
-    for (int idx = tid; idx < IT * IT * KC; idx += 256) {
+    for (int idx = tid; idx < ITH * ITW * KC; idx += 256) {
       const int ci = idx % KC, pix = idx / KC;
-      const int gy = iy0 + pix / IT, gx = ix0 + pix % IT;
+      const int gy = iy0 + pix / ITW, gx = ix0 + pix % ITW;
       float v = 0.f;
       if (gy >= 0 && gy < p.Hin && gx >= 0 && gx < p.Win && c0 + ci < p.cin) {
         const size_t gi = (((size_t)n * p.Hin + gy) * p.Win + gx) * p.in_C + p.in_c_off + c0 + ci;
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvParams p) {
       }
       s_in[pix][ci] = v;
     }
-    for (int idx = tid; idx < KS * KS * KC * 64; idx += 256) {
+    for (int idx = tid; idx < KH * KW * KC * 64; idx += 256) {
       const int co = idx & 63, ci = (idx >> 6) % KC, tap = idx / (64 * KC);
       float v = 0.f;
       if (c0 + ci < p.cin) v = p.w[((size_t)tap * p.cin + c0 + ci) * p.coutPad + co0 + co];
@@ -64,15 +64,15 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvParams p) {
     }
     __syncthreads();
 #pragma unroll
-    for (int ky = 0; ky < KS; ++ky) {
+    for (int ky = 0; ky < KH; ++ky) {
 #pragma unroll
-      for (int kx = 0; kx < KS; ++kx) {
+      for (int kx = 0; kx < KW; ++kx) {
 #pragma unroll
         for (int ci = 0; ci < KC; ++ci) {
-          const float4 w4 = *reinterpret_cast<const float4*>(&s_w[ky * KS + kx][ci][tc * 4]);
+          const float4 w4 = *reinterpret_cast<const float4*>(&s_w[ky * KW + kx][ci][tc * 4]);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float a = s_in[(prow * STRIDE + ky) * IT + (pcol + i) * STRIDE + kx][ci];
+            const float a = s_in[(prow * STRIDE + ky) * ITW + (pcol + i) * STRIDE + kx][ci];
             acc[i][0] = fmaf(a, w4.x, acc[i][0]);
             acc[i][1] = fmaf(a, w4.y, acc[i][1]);
             acc[i][2] = fmaf(a, w4.z, acc[i][2]);
@@ -195,12 +195,21 @@ int launch_conv_simt(const ConvParams& p, int ksize, int stride, cudaStream_t st
     B2R_CUDA_OK(cudaGetLastError());
     return B200ROMP_OK;
   }
+  if (ksize == 13 && stride == 1 && p.up == 1) {
+    // Conv1d(k=3) along W (bev/model.py:19-22): rows are independent, so the batch folds into the row index
+    ConvParams q = p;
+    q.B = 1; q.Hin = p.B * p.Hin; q.Hout = p.B * p.Hout;
+    dim3 g(((q.Hout + 7) / 8) * ((q.Wout + 7) / 8), (q.cout + 63) / 64, 1);
+    conv_simt_kernel<1, 3, 1><<<g, 256, 0, stream>>>(q);
+    B2R_CUDA_OK(cudaGetLastError());
+    return B200ROMP_OK;
+  }
   dim3 grid(((p.Hout + 7) / 8) * ((p.Wout + 7) / 8), (p.cout + 63) / 64, p.B);
   dim3 block(256);
-  if (ksize == 3 && stride == 1) conv_simt_kernel<3, 1><<<grid, block, 0, stream>>>(p);
-  else if (ksize == 3 && stride == 2) conv_simt_kernel<3, 2><<<grid, block, 0, stream>>>(p);
-  else if (ksize == 1 && stride == 1) conv_simt_kernel<1, 1><<<grid, block, 0, stream>>>(p);
-  else if (ksize == 1 && stride == 2) conv_simt_kernel<1, 2><<<grid, block, 0, stream>>>(p);
+  if (ksize == 3 && stride == 1) conv_simt_kernel<3, 3, 1><<<grid, block, 0, stream>>>(p);
+  else if (ksize == 3 && stride == 2) conv_simt_kernel<3, 3, 2><<<grid, block, 0, stream>>>(p);
+  else if (ksize == 1 && stride == 1) conv_simt_kernel<1, 1, 1><<<grid, block, 0, stream>>>(p);
+  else if (ksize == 1 && stride == 2) conv_simt_kernel<1, 1, 2><<<grid, block, 0, stream>>>(p);
   else {
     set_error("conv_simt: unsupported ksize=%d stride=%d", ksize, stride);
     return B200ROMP_EINVAL;

@@ -252,9 +252,9 @@ static int dispatch(const TcConvPlan& plan, const ConvParams& p, cudaStream_t st
     if (plan.ksplit == 1) return launch_inst<K, C, N, PER_TAP, 1>(plan, p, stream, attr);            \
     return launch_inst<K, C, N, PER_TAP, tc_ksplit(K * K * (C / 16), N)>(plan, p, stream, attr);      \
   }
-  B2R_CASE(3, 32, 32) B2R_CASE(3, 64, 64) B2R_CASE(3, 128, 64) B2R_CASE(3, 256, 32)
+  B2R_CASE(3, 32, 32) B2R_CASE(3, 32, 64) B2R_CASE(3, 64, 64) B2R_CASE(3, 128, 64) B2R_CASE(3, 256, 32)
   B2R_CASE(1, 64, 32) B2R_CASE(1, 64, 64) B2R_CASE(1, 128, 32) B2R_CASE(1, 128, 64) B2R_CASE(1, 256, 32)
-  B2R_CASE(1, 256, 64)
+  B2R_CASE(1, 256, 64) B2R_CASE(1, 32, 64) B2R_CASE(1, 32, 32)
 #undef B2R_CASE
   set_error("conv_tc: no instantiation for k%d cin%d nt%d", ks, plan.cin, plan.nt);
   return B200ROMP_EINVAL;

@@ -80,9 +80,9 @@ static int fill_params(b200romp_net* net, const Op& op, int batch, ConvParams* o
   p.w = op.d_w_simt; p.bias = op.d_bias;
   p.B = batch;
   p.Hin = ti.H; p.Win = ti.W; p.in_C = ti.C; p.in_c_off = d.in_c_off; p.cin = d.cin;
-  const int pad = d.ksize / 2;
-  p.Hout = (ti.H + 2 * pad - d.ksize) / d.stride + 1;
-  p.Wout = (ti.W + 2 * pad - d.ksize) / d.stride + 1;
+  const int kh = d.ksize == 13 ? 1 : d.ksize, kw = d.ksize == 13 ? 3 : d.ksize;   // 13 = Conv1d 1x3
+  p.Hout = (ti.H + 2 * (kh / 2) - kh) / d.stride + 1;
+  p.Wout = (ti.W + 2 * (kw / 2) - kw) / d.stride + 1;
   p.out_C = to.C; p.out_c_off = d.out_c_off; p.cout = d.cout; p.coutPad = op.coutPad;
   p.up = d.upsample;
   if (d.res >= 0) {
@@ -104,15 +104,16 @@ static int validate_desc(const std::vector<Tensor>& T, const b200romp_conv_desc&
   const int res_c_off = d.res_c_off;
   auto ok_id = [&](int id) { return id >= 0 && id < (int)T.size(); };
   B2R_REQUIRE(ok_id(d.in) && ok_id(d.out) && (d.res == -1 || ok_id(d.res)), "conv: bad tensor id");
-  B2R_REQUIRE((d.ksize == 1 || d.ksize == 3) && (d.stride == 1 || d.stride == 2), "conv: ksize/stride unsupported");
+  B2R_REQUIRE((d.ksize == 1 || d.ksize == 3 || (d.ksize == 13 && d.stride == 1 && d.upsample == 1)) && (d.stride == 1 || d.stride == 2),
+              "conv: ksize/stride unsupported");
   B2R_REQUIRE(d.upsample == 1 || d.upsample == 2 || d.upsample == 4 || d.upsample == 8, "conv: upsample must be 1,2,4,8");
   const Tensor& ti = T[d.in];
   const Tensor& to = T[d.out];
   B2R_REQUIRE(!ti.nchw, "conv: NCHW inputs unsupported");
   B2R_REQUIRE(d.cin > 0 && d.in_c_off >= 0 && d.in_c_off + d.cin <= ti.C, "conv: input channel slice out of range");
   B2R_REQUIRE(d.cout > 0 && d.out_c_off >= 0 && d.out_c_off + d.cout <= to.C, "conv: output channel slice out of range");
-  const int pad = d.ksize / 2;
-  const int Ho = (ti.H + 2 * pad - d.ksize) / d.stride + 1, Wo = (ti.W + 2 * pad - d.ksize) / d.stride + 1;
+  const int kh = d.ksize == 13 ? 1 : d.ksize, kw = d.ksize == 13 ? 3 : d.ksize;
+  const int Ho = (ti.H + 2 * (kh / 2) - kh) / d.stride + 1, Wo = (ti.W + 2 * (kw / 2) - kw) / d.stride + 1;
   B2R_REQUIRE(Ho * d.upsample == to.H && Wo * d.upsample == to.W, "conv: output tensor is %dx%d, op produces %dx%d",
               to.H, to.W, Ho * d.upsample, Wo * d.upsample);
   B2R_REQUIRE(ti.dtype != B200ROMP_U8 || d.input_norm, "conv: u8 input requires input_norm");
@@ -193,7 +194,7 @@ int b200romp_net_add_conv(b200romp_net* net, const b200romp_conv_desc* desc, con
   if (rc) return rc;
   Op op;
   op.d = *desc;
-  const size_t nw = (size_t)desc->cout * desc->cin * desc->ksize * desc->ksize;
+  const size_t nw = (size_t)desc->cout * desc->cin * (desc->ksize == 13 ? 3 : desc->ksize * desc->ksize);
   op.w_host.assign(weight, weight + nw);
   op.b_host.assign(desc->cout, 0.f);
   if (bias) op.b_host.assign(bias, bias + desc->cout);
@@ -203,7 +204,7 @@ int b200romp_net_add_conv(b200romp_net* net, const b200romp_conv_desc* desc, con
 
 static int upload_simt_weights(b200romp_net* net, Op& op) {
   const b200romp_conv_desc& d = op.d;
-  const int taps = d.ksize * d.ksize;
+  const int taps = d.ksize == 13 ? 3 : d.ksize * d.ksize;
   op.coutPad = (d.cout + 63) / 64 * 64;
   std::vector<float> packed((size_t)taps * d.cin * op.coutPad, 0.f);
   for (int co = 0; co < d.cout; ++co)

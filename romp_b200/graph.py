@@ -1,11 +1,11 @@
-"""Host-side graph builder for seam S1: turns the reference's ROMPv1 state dict into the fused conv ops
+"""Host-side graph builder for seam S1: turns the reference's state dicts (ROMPv1 / BEVv1) into the fused conv ops
 executed by libb200romp (b200romp_net_*).
 
 It mirrors the *structure* of simple_romp/romp/model.py (HigherResolutionNet :246-417, HighResolutionModule
-:129-244, Bottleneck :85-123, BasicBlock :54-83, ROMPv1 head :420-481) and consumes exactly the
-reference's state-dict keys, so a released ``ROMP.pkl`` loads unchanged.  Work done here is weight
-preprocessing only (BatchNorm folding, constant folding of the coord-map channels); every per-frame FLOP
-runs in the CUDA library.
+:129-244, Bottleneck :85-123, BasicBlock :54-83, ROMPv1 head :420-481) and of simple_romp/bev/model.py
+(BEVv1 heads :142-186) and consumes exactly the reference's state-dict keys, so released checkpoints load
+unchanged.  Work done here is weight preprocessing only (BatchNorm folding, constant folding of the coord-map
+channels); every per-frame FLOP runs in the CUDA library.
 """
 from __future__ import annotations
 
@@ -32,11 +32,15 @@ def fold_bn(sd, conv, bn):
     mean = np.asarray(sd[bn + ".running_mean"], np.float64)
     var = np.asarray(sd[bn + ".running_var"], np.float64)
     scale = g / np.sqrt(var + BN_EPS)
-    return (w * scale[:, None, None, None]).astype(np.float32), ((b - mean) * scale + beta).astype(np.float32)
+    return (w * scale.reshape((-1,) + (1,) * (w.ndim - 1))).astype(np.float32), ((b - mean) * scale + beta).astype(np.float32)
 
 
 def round_bf16(a):
     return torch.from_numpy(np.ascontiguousarray(a)).bfloat16().float().numpy()
+
+
+def to_numpy_sd(sd):
+    return {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in sd.items()}
 
 
 class NetBuilder:
@@ -74,9 +78,13 @@ class NetBuilder:
 
     def conv(self, x, w, b, *, stride=1, relu=False, res=None, res_c_off=0, res_broadcast=0, up=1, out=None,
              out_c_off=0, out_dtype=None, in_c_off=0, input_norm=0, pow_channel=-1, engine=None, name=None):
-        cout, cin, k, _ = w.shape
+        """w: OIHW (Conv2d) or [O,I,3] (Conv1d along W, ksize code 13)."""
+        conv1d = w.ndim == 3
+        cout, cin = w.shape[0], w.shape[1]
+        k = 13 if conv1d else w.shape[2]
+        kh, kw = (1, 3) if conv1d else (k, k)
         H, W, _, _ = self.shape[x]
-        Ho, Wo = ((H + 2 * (k // 2) - k) // stride + 1) * up, ((W + 2 * (k // 2) - k) // stride + 1) * up
+        Ho, Wo = ((H + 2 * (kh // 2) - kh) // stride + 1) * up, ((W + 2 * (kw // 2) - kw) // stride + 1) * up
         if out is None:
             out = self.tensor(Ho, Wo, cout, out_dtype, name=name)
         d = ConvDesc(x, in_c_off, out, out_c_off, -1 if res is None else res, res_c_off, res_broadcast, cin, cout, k,
@@ -88,7 +96,7 @@ class NetBuilder:
         _lib.check(self.lib.b200romp_net_add_conv(
             self.net, C.byref(d), w.ctypes.data_as(C.POINTER(C.c_float)),
             None if bp is None else bp.ctypes.data_as(C.POINTER(C.c_float))), "add_conv")
-        self.flops_per_frame += 2 * cout * cin * k * k * (Ho // up) * (Wo // up)
+        self.flops_per_frame += 2 * cout * cin * kh * kw * (Ho // up) * (Wo // up)
         return out
 
     def finalize(self, max_batch):
@@ -106,13 +114,8 @@ def coord_maps(size=128):
     return torch.stack([r.view(1, size).expand(size, size), r.view(size, 1).expand(size, size)])[None].contiguous()
 
 
-def build_romp(sd, device=0, precision="bf16", in_dtype=U8, max_batch=64, engine=_lib.ENGINE_AUTO):
-    """ROMPv1 (HRNet-32 + 3 heads) as a libb200romp conv graph.
-
-    Returns (builder, io) with io = dict(frames=, center_maps=, params_maps=) external tensor ids.
-    """
-    sd = {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in sd.items()}
-    nb = NetBuilder(device, precision, engine)
+def build_backbone(nb: NetBuilder, sd, in_dtype):
+    """HigherResolutionNet (model.py:336-417) -> (frames tensor id, [B,128,128,32] feature tensor id)."""
     act = nb.act
 
     def cb(x, conv, bn, **kw):
@@ -130,9 +133,9 @@ def build_romp(sd, device=0, precision="bf16", in_dtype=U8, max_batch=64, engine
         res = cb(x, q + "downsample.0", q + "downsample.1") if (q + "downsample.0.weight") in sd else x
         x = cb(y, q + "conv3", q + "bn3", relu=True, res=res)
 
-    def basic_block(x, q, in_c_off=0, res_c_off=0):
-        t = cb(x, q + "conv1", q + "bn1", relu=True, in_c_off=in_c_off)
-        return cb(t, q + "conv2", q + "bn2", relu=True, res=x, res_c_off=res_c_off)
+    def basic_block(x, q):
+        t = cb(x, q + "conv1", q + "bn1", relu=True)
+        return cb(t, q + "conv2", q + "bn2", relu=True, res=x)
 
     def hr_module(xs, q, nbr, multi=True):
         """HighResolutionModule.forward model.py:226-244; fuse sum kept in fp32 until the final ReLU."""
@@ -168,8 +171,26 @@ def build_romp(sd, device=0, precision="bf16", in_dtype=U8, max_batch=64, engine
     xs = xs + [cb(xs[-1], p + "transition3.3.0.0", p + "transition3.3.0.1", stride=2, relu=True)]    # :409-414
     for m in range(3):
         xs = hr_module(xs, f"{p}stage4.{m}.", 4, multi=(m != 2))
-    feat = xs[0]
-    nb.names["backbone_out"] = feat
+    nb.names["backbone_out"] = xs[0]
+    return frames, xs[0]
+
+
+def build_romp(sd, device=0, precision="bf16", in_dtype=U8, max_batch=64, engine=_lib.ENGINE_AUTO):
+    """ROMPv1 (HRNet-32 + 3 heads) as a libb200romp conv graph.
+
+    Returns (builder, io) with io = dict(frames=, center_maps=, params_maps=) external tensor ids.
+    """
+    sd = to_numpy_sd(sd)
+    nb = NetBuilder(device, precision, engine)
+    frames, feat = build_backbone(nb, sd, in_dtype)
+
+    def cb(x, conv, bn, **kw):
+        w, b = fold_bn(sd, conv, bn)
+        return nb.conv(x, w, b, **kw)
+
+    def basic_block(x, q, in_c_off=0, res_c_off=0):
+        t = cb(x, q + "conv1", q + "bn1", relu=True, in_c_off=in_c_off)
+        return cb(t, q + "conv2", q + "bn2", relu=True, res=x, res_c_off=res_c_off)
 
     # ---- heads (model.py:445-481).  The three head-in convs 34->64 (3x3, s2, bias, BN, ReLU) are fused into
     # one 32->192 conv; the two constant coord channels (model.py:473) become a per-pixel bias map.
@@ -197,3 +218,75 @@ def build_romp(sd, device=0, precision="bf16", in_dtype=U8, max_batch=64, engine
             nb.conv(y, w, b, out=center_maps)
     nb.finalize(max_batch)
     return nb, dict(frames=frames, center_maps=center_maps, params_maps=params_maps)
+
+
+def build_bev(sd, device=0, precision="bf16", in_dtype=U8, max_batch=32, engine=_lib.ENGINE_AUTO):
+    """BEVv1's convolutional part as two conv graphs (bev/model.py:142-186,232-250).
+
+    G1: backbone -> det_head (maps_fv [B,4,128,128] fp32 NCHW), param_head (front-view features [B,128,128,128]),
+        bv_pre_layers (img_feats [B,128,128,16]).
+    G2: bv_out_layers = 3 x BasicBlock_1D (Conv1d k3 as ksize code 13) on the [B,1,128,2560] bird's-eye input that
+        b200romp_bev_bv_input assembles from G1's outputs -> [B,1,128,128].
+    Returns (g1, io1, g2, io2).
+    """
+    sd = to_numpy_sd(sd)
+    g1 = NetBuilder(device, precision, engine)
+    frames, feat = build_backbone(g1, sd, in_dtype)
+
+    def head_block(x, q, out=None):
+        """BasicBlock(32->128) whose residual is a biased 1x1 conv without BN (bev/model.py:154-156)."""
+        w, b = fold_bn(sd, q + "conv1", q + "bn1")
+        t = g1.conv(x, w, b, relu=True)
+        wd, bd = fold_bn(sd, q + "downsample", None)
+        res = g1.conv(x, wd, bd)
+        w, b = fold_bn(sd, q + "conv2", q + "bn2")
+        return g1.conv(t, w, b, relu=True, res=res, out=out)
+
+    maps_fv = g1.tensor(128, 128, 4, F32, nchw=1, external=1, name="maps_fv")
+    y = head_block(feat, "det_head.0.0.")
+    w, b = fold_bn(sd, "det_head.1", None)
+    g1.conv(y, w, b, out=maps_fv)                                                     # center_fv | cam_offset(3)
+    fv = g1.tensor(128, 128, 128, None, external=1, name="fv_feats")
+    head_block(feat, "param_head.0.0.", out=fv)
+    x = feat
+    for i in (0, 3):                                                                   # bv_pre_layers, :166-175
+        w, b = fold_bn(sd, f"bv_pre_layers.{i}", f"bv_pre_layers.{i + 1}")
+        x = g1.conv(x, w, b, relu=True, engine=_lib.ENGINE_SIMT)
+    img_feats = g1.tensor(128, 128, 16, None, external=1, name="img_feats")
+    w, b = fold_bn(sd, "bv_pre_layers.6", "bv_pre_layers.7")
+    g1.conv(x, w, b, relu=True, out=img_feats, engine=_lib.ENGINE_SIMT)
+    g1.finalize(max_batch)
+
+    g2 = NetBuilder(device, precision, _lib.ENGINE_SIMT)
+    bv_in = g2.tensor(1, 128, 2560, None, external=1, name="bv_in")
+    y = bv_in
+    bv_out = g2.tensor(1, 128, 128, None, external=1, name="bv_out")
+    for i in range(3):                                                                 # BasicBlock_1D x3, :179-182,24-45
+        q = f"bv_out_layers.{i}."
+        w, b = fold_bn(sd, q + "conv1", q + "bn1")
+        y = g2.conv(y, w, b, relu=True)
+        w, b = fold_bn(sd, q + "conv2", q + "bn2")
+        y = g2.conv(y, w, b, relu=True, out=bv_out if i == 2 else None)
+    g2.finalize(max_batch)
+    return (g1, dict(frames=frames, maps_fv=maps_fv, fv_feats=fv, img_feats=img_feats),
+            g2, dict(bv_in=bv_in, bv_out=bv_out))
+
+
+def bev_weights(sd):
+    """Host arrays for b200romp_bev_create: BatchNorm3d-folded refiners, coord map, anchors, embedding, MLP."""
+    from .synth import bev_cam3dmap_anchor
+    sd = to_numpy_sd(sd)
+
+    def ref(name, c):
+        w1, b1 = fold_bn(sd, f"{name}.0.conv1", f"{name}.0.bn1")
+        w2, b2 = fold_bn(sd, f"{name}.0.conv2", f"{name}.0.bn2")
+        return np.concatenate([w1.reshape(-1), b1.reshape(-1), w2.reshape(-1), b2.reshape(-1)]).astype(np.float32)
+
+    out = {"center_ref": ref("center_map_refiner", 1), "cam_ref": ref("cam_map_refiner", 3),
+           "coordmap": np.ascontiguousarray(sd["coordmap_3d"], np.float32).reshape(-1),
+           "anchors": bev_cam3dmap_anchor(60, 128), "embed": np.ascontiguousarray(sd["position_embeddings.weight"], np.float32)}
+    for i, k in zip((0, 3, 6), ("0", "1", "2")):
+        out["w" + k] = np.ascontiguousarray(sd[f"transformer.{i}.weight"], np.float32)
+        out["b" + k] = np.ascontiguousarray(sd[f"transformer.{i}.bias"], np.float32)
+    assert out["center_ref"].size == 56 and out["cam_ref"].size == 168
+    return out
