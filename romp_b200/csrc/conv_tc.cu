@@ -269,7 +269,7 @@ int tc_conv_prepare(const ConvParams& p, int ksize, int stride, const float* w_o
     return B200ROMP_ECUDA;
   }
   const bool per_tap = false;   // the per-tap TMA variant (PER_TAP=true) was only the bring-up fallback
-  { const char* e = getenv("B200ROMP_TC_KSPLIT"); plan->ksplit = (e && e[0] == '4') ? 0 : 1;   // K-split accumulators measured slower (tools/mma_bench.cu): off by default }
+  { const char* e = getenv("B200ROMP_TC_KSPLIT"); plan->ksplit = (e && e[0] == '4') ? 0 : 1; }   /* K-split measured slower: off by default */
   const int taps = ksize * ksize;
   const int cw = p.cin < 64 ? p.cin : 64, kch = p.cin / cw, rowb = cw * 2;
   // N tile: weights must stay resident next to >= 2 pipeline stages

@@ -221,7 +221,7 @@ int tc_s2_prepare(const ConvParams& p, const float* w_oihw, int sm_count, TcConv
   }
   plan->stages = std::min(4, (budget - bbytes(nt)) / stage_bytes);
   plan->kind = 32;
-  { const char* e = getenv("B200ROMP_TC_KSPLIT"); plan->ksplit = (e && e[0] == '4') ? 0 : 1;   // K-split accumulators measured slower (tools/mma_bench.cu): off by default }
+  { const char* e = getenv("B200ROMP_TC_KSPLIT"); plan->ksplit = (e && e[0] == '4') ? 0 : 1; }   /* K-split measured slower: off by default */
   plan->cin = p.cin; plan->cout = p.cout; plan->nt = nt;
   plan->grid_y = p.cout / nt;
   plan->grid_x = std::max(1, sm_count / plan->grid_y);
