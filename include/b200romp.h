@@ -157,7 +157,7 @@ int b200romp_project(const float* joints /*[n,71,3]*/, const float* verts /*[n,6
 typedef struct b200romp_bev b200romp_bev;
 typedef struct b200romp_bev_weights {   /* host fp32 arrays */
   const float* center_ref;  /* [56]  center_map_refiner, BatchNorm3d folded: w1[27], b1, w2[27], b2   (bev/model.py:185)  */
-  const float* cam_ref;     /* [168] cam_map_refiner: w1[3][3][27], b1[3], w2[3][3][27], b2[3]          (bev/model.py:186)  */
+  const float* cam_ref;     /* [492] cam_map_refiner: w1[3][3][27], b1[3], w2[3][3][27], b2[3]          (bev/model.py:186)  */
   const float* coordmap;    /* [64,128,128,3] coordmap_3d buffer                                       (bev/model.py:128)  */
   const float* anchors;     /* [64]  cam3dmap_anchor                                                   (bev/model.py:77-87) */
   const float* embed;       /* [128,128] position_embeddings.weight                                    (bev/model.py:132)  */

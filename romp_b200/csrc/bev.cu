@@ -30,7 +30,7 @@ constexpr float kTanFov = 0.57735026919f;   // tan(radians(60/2)), bev/post_pars
 
 struct BevDev {
   const float* center_ref;   // [56]  w1[27] b1 w2[27] b2   (BatchNorm3d folded)
-  const float* cam_ref;      // [168] w1[3][3][27] b1[3] w2[3][3][27] b2[3]
+  const float* cam_ref;      // [492] w1[3][3][27] b1[3] w2[3][3][27] b2[3]
   const float* coordmap;     // [64][128][128][3]
   const float* anchors;      // [64]
   const float* embed;        // [128][128]
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(256) bev_regress_kernel(BevDev m, const float*
     const int nz = nb / 9 - 1, ny = (nb / 3) % 3 - 1, nx = nb % 3 - 1;
     float acc = 0.f;
     if (z + nz >= 0 && z + nz < kD && y + ny >= 0 && y + ny < kS && x + nx >= 0 && x + nx < kS) {
-      acc = m.cam_ref[81 + c1];
+      acc = m.cam_ref[243 + c1];
       for (int c0 = 0; c0 < 3; ++c0)
         for (int tz = 0; tz < 3; ++tz)
           for (int ty = 0; ty < 3; ++ty)
@@ -211,9 +211,9 @@ __global__ void __launch_bounds__(256) bev_regress_kernel(BevDev m, const float*
   }
   __syncthreads();
   if (tid < 3) {
-    float acc = m.cam_ref[165 + tid];
+    float acc = m.cam_ref[489 + tid];
     for (int c1 = 0; c1 < 3; ++c1)
-      for (int t = 0; t < 27; ++t) acc = fmaf(m.cam_ref[84 + (tid * 3 + c1) * 27 + t], s_t1[c1][t], acc);
+      for (int t = 0; t < 27; ++t) acc = fmaf(m.cam_ref[246 + (tid * 3 + c1) * 27 + t], s_t1[c1][t], acc);
     s_cam[tid] = acc + s_in[tid][62];                                 // residual of BasicBlock_3D, centre voxel
   }
   __syncthreads();
@@ -435,7 +435,7 @@ b200romp_bev* b200romp_bev_create(int device, const b200romp_bev_weights* w) {
   };
   BevDev& d = h->dev;
   d.center_ref = up(h, w->center_ref, 56, &ok);
-  d.cam_ref = up(h, w->cam_ref, 168, &ok);
+  d.cam_ref = up(h, w->cam_ref, 492, &ok);
   d.coordmap = up(h, w->coordmap, (size_t)kVol * 3, &ok);
   d.anchors = up(h, w->anchors, 64, &ok);
   d.embed = up(h, w->embed, 128 * 128, &ok);

@@ -288,5 +288,5 @@ def bev_weights(sd):
     for i, k in zip((0, 3, 6), ("0", "1", "2")):
         out["w" + k] = np.ascontiguousarray(sd[f"transformer.{i}.weight"], np.float32)
         out["b" + k] = np.ascontiguousarray(sd[f"transformer.{i}.bias"], np.float32)
-    assert out["center_ref"].size == 56 and out["cam_ref"].size == 168
+    assert out["center_ref"].size == 56 and out["cam_ref"].size == 492
     return out
