@@ -420,3 +420,46 @@ def mpjpe_mm(j_a, j_b):
     a = a - a[:, :1]
     b = b - b[:, :1]
     return float(torch.norm(a - b, dim=-1).mean() * 1000.0)
+
+
+# ----------------------------------------------------------------------------------------------
+# cfg1: ROMP with the ResNet-50 backbone (romp/lib/models/resnet_50.py:19-120) - CPU reference plumbing only
+# ----------------------------------------------------------------------------------------------
+def resnet50_forward(sd, frames_nhwc):
+    """ResNet_50.forward (:55-63): /255 + ImageNet mean/std (:32-38), 7x7 s2 stem, maxpool 3x3 s2, [3,4,6,3] bottlenecks
+    (stride on the 3x3 conv), three ConvTranspose2d(4,2,1)+BN+ReLU 2048->256->128->64.  -> [B,64,128,128]."""
+    x = frames_nhwc.permute(0, 3, 1, 2) / 255.0
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    x = (x - mean) / std
+    p = "backbone."
+    w = sd[p + "conv1.weight"]
+    x = F.conv2d(x, w, None, 2, 3)
+    x = F.relu(F.batch_norm(x, sd[p + "bn1.running_mean"], sd[p + "bn1.running_var"], sd[p + "bn1.weight"], sd[p + "bn1.bias"], False, 0.0, BN_EPS))
+    x = F.max_pool2d(x, 3, 2, 1)
+    for li, blocks in enumerate((3, 4, 6, 3), start=1):
+        for b in range(blocks):
+            q = f"{p}layer{li}.{b}."
+            stride = 2 if (li > 1 and b == 0) else 1
+            y = conv_bn(sd, q + "conv1", q + "bn1", x, relu=True)
+            y = conv_bn(sd, q + "conv2", q + "bn2", y, stride=stride, relu=True)
+            y = conv_bn(sd, q + "conv3", q + "bn3", y)
+            res = x
+            if (q + "downsample.0.weight") in sd:
+                res = conv_bn(sd, q + "downsample.0", q + "downsample.1", x, stride=stride)
+            x = F.relu(y + res)
+    for i in range(3):
+        x = F.conv_transpose2d(x, sd[f"{p}deconv_layers.{3 * i}.weight"], None, stride=2, padding=1)
+        bn = f"{p}deconv_layers.{3 * i + 1}"
+        x = F.relu(F.batch_norm(x, sd[bn + ".running_mean"], sd[bn + ".running_var"], sd[bn + ".weight"], sd[bn + ".bias"], False, 0.0, BN_EPS))
+    return x
+
+
+@torch.no_grad()
+def romp_resnet50_maps(sd, frames_nhwc):
+    """ROMP head (same layout as ROMPv1, 64+2 input channels) on the ResNet-50 features + cam-scale pow."""
+    sd = to_torch_sd(sd)
+    center, params = romp_head(sd, resnet50_forward(sd, _t(frames_nhwc).float()))
+    params = params.clone()
+    params[:, 0] = torch.pow(1.1, params[:, 0])
+    return center, params

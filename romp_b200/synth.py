@@ -322,3 +322,57 @@ def bev_state_dict(seed: int = 0, gain: float = 0.55):
         elif kind == "bn_n":
             sd[name] = np.array(1, dtype=np.int64)
     return sd
+
+
+# --------------------------------------------------------------------------------------
+# ResNet-50 backbone variant of ROMP (BASELINE.json configs[0]; romp/lib/models/resnet_50.py:19-120)
+# --------------------------------------------------------------------------------------
+def resnet50_param_specs():
+    s = []
+    _conv(s, "backbone.conv1", 64, 3, 7); _bn(s, "backbone.bn1", 64)
+    inplanes = 64
+    for li, (planes, blocks) in enumerate(((64, 3), (128, 4), (256, 6), (512, 3)), start=1):
+        for b in range(blocks):
+            q = f"backbone.layer{li}.{b}."
+            _conv(s, q + "conv1", planes, inplanes, 1); _bn(s, q + "bn1", planes)
+            _conv(s, q + "conv2", planes, planes, 3); _bn(s, q + "bn2", planes)
+            _conv(s, q + "conv3", planes * 4, planes, 1); _bn(s, q + "bn3", planes * 4)
+            if b == 0:
+                _conv(s, q + "downsample.0", planes * 4, inplanes, 1); _bn(s, q + "downsample.1", planes * 4)
+            inplanes = planes * 4
+    cin = 2048
+    for i, planes in enumerate((256, 128, 64)):
+        s.append((f"backbone.deconv_layers.{3 * i}.weight", (cin, planes, 4, 4), "conv_w"))   # ConvTranspose2d: [in,out,k,k]
+        _bn(s, f"backbone.deconv_layers.{3 * i + 1}", planes)
+        cin = planes
+    for h in (1, 2, 3):                      # ROMP head on 64 + 2 coord channels (romp/lib/models/romp_model.py)
+        q = f"final_layers.{h}."
+        _conv(s, q + "0.0", 64, 66, 3, bias=True); _bn(s, q + "0.1", 64)
+        for blk in range(2):
+            r = f"{q}1.{blk}.0."
+            _conv(s, r + "conv1", 64, 64, 3); _bn(s, r + "bn1", 64)
+            _conv(s, r + "conv2", 64, 64, 3); _bn(s, r + "bn2", 64)
+        _conv(s, q + "2", HEAD_OUT[h], 64, 1, bias=True)
+    return s
+
+
+def resnet50_state_dict(seed: int = 0, gain: float = 0.8):
+    rng = np.random.RandomState(seed + 50)
+    sd = {}
+    for spec in resnet50_param_specs():
+        name, shape, kind = spec[0], spec[1], spec[2]
+        if kind == "conv_w":
+            fan_in = int(np.prod(shape[1:])) if "deconv" not in name else shape[0] * 4   # 2x2 of the 4x4 taps hit each output
+            bound = gain * np.sqrt(3.0 / fan_in)
+            sd[name] = rng.uniform(-bound, bound, size=shape).astype(np.float32)
+        elif kind == "conv_b":
+            sd[name] = (rng.uniform(-1, 1, size=shape) / np.sqrt(spec[3])).astype(np.float32)
+        elif kind == "bn_w":
+            sd[name] = rng.uniform(0.5, 1.5, size=shape).astype(np.float32)
+        elif kind in ("bn_b", "bn_m"):
+            sd[name] = rng.normal(0.0, 0.1, size=shape).astype(np.float32)
+        elif kind == "bn_v":
+            sd[name] = rng.uniform(0.5, 1.5, size=shape).astype(np.float32)
+        elif kind == "bn_n":
+            sd[name] = np.array(1, dtype=np.int64)
+    return sd

@@ -105,3 +105,21 @@ def test_cam_trans_closed_form_matches_reference_fallback(golden_dir):
     ref = z["cam_trans_np"]
     assert (ref == -1).all(1).any() or True
     assert np.abs(pr["cam_trans"].numpy() - ref).max() < 2e-4 * max(1.0, np.abs(ref).max())
+
+
+def test_cfg1_resnet50_plumbing(golden_dir):
+    """BASELINE.json configs[0]: ROMP with the ResNet-50 backbone, one 512x512 frame, one planted person, CPU only.
+    The backbone restatement is pinned to the reference's romp/lib/models/resnet_50.py (fixture made by importing it)."""
+    z = g(golden_dir, "resnet50_seed0.npz")
+    sd = synth.resnet50_state_dict(0)
+    frames = synth.synthetic_frames(1, seed=0)
+    feat = O.resnet50_forward(O.to_torch_sd(sd), torch.from_numpy(frames).float())
+    assert np.abs(feat[0, 0].detach().numpy() - z["feat_ch0"]).max() < 2e-5
+    assert np.abs(feat.mean((0, 2, 3)).detach().numpy() - z["feat_mean"]).max() < 1e-5
+    center, params = O.romp_resnet50_maps(sd, frames)
+    assert center.shape == (1, 1, 64, 64) and params.shape == (1, 145, 64, 64)
+    planted = np.zeros((1, 1, 64, 64), np.float32); planted[0, 0, 30, 20] = 0.8
+    out = O.parsing_outputs(planted, params, 0.25)
+    assert len(out["cam"]) == 1 and out["center_preds"].tolist() == [[160, 240]]
+    v, j = O.smpl_forward(synth.smpl_pack(0), out["smpl_betas"], out["smpl_thetas"])
+    assert v.shape == (1, 6890, 3) and j.shape == (1, 71, 3) and torch.isfinite(v).all()
