@@ -195,7 +195,7 @@ def run_ours(args):
     w0 = time.perf_counter()
     # public streaming API: per step H2D of that step's pinned frames, the whole path, D2H of the result dict;
     # copies of neighbouring steps overlap the kernels (forward_batches), results are consumed in order
-    for res in model.forward_batches((frames_host for _ in range(args.steps)), center_override=planted):
+    for res in model.forward_batches((frames_host for _ in range(args.steps)), center_override=planted, to_numpy=(world == 1)):
         out = gather(res)
     barrier()
     t_e2e = time.perf_counter() - w0

@@ -279,7 +279,7 @@ class ROMP(torch.nn.Module):
         return out
 
     @torch.no_grad()
-    def forward_batches(self, batches, offsets=None, center_override=None):
+    def forward_batches(self, batches, offsets=None, center_override=None, to_numpy=True):
         """Pipelined streaming over an iterable of host frame batches (video): yields one result dict (or None) per
         batch, in order.  H2D of batch i+1 (copy stream) and D2H of batch i-1 (read-back stream) overlap the
         kernels of batch i; the only host waits are on the person-count event of an already finished batch."""
@@ -305,14 +305,14 @@ class ROMP(torch.nn.Module):
                 self.run_post(B, off, center_override, slot)
                 slot["done"].record(self.stream)
             if pending is not None:
-                yield self._read_back(pending)
+                yield self._read_back(pending, to_numpy)
             pending = slot
         if pending is not None:
-            yield self._read_back(pending)
+            yield self._read_back(pending, to_numpy)
 
-    def _read_back(self, slot):
+    def _read_back(self, slot, to_numpy=True):
         self.d2h_stream.wait_event(slot["done"])
-        return self.collect(True, slot, self.d2h_stream)
+        return self.collect(to_numpy, slot, self.d2h_stream)   # device views stay valid until the slot's next batch
 
     @torch.no_grad()
     def forward(self, image, signal_ID=0, **kwargs):

@@ -62,20 +62,53 @@ def all_gather_outputs(out, frame_offset: int, world: int, to_numpy: bool = True
     nmax, width = int(counts[:, 0].max()), int(counts[:, 1].max())
     if nmax == 0:
         return None
-    layouts = [None] * world
-    dist.all_gather_object(layouts, layout, group=group)
-    layout = next(l for l in layouts if l is not None)
+    if layout is None and width == DEFAULT_WIDTH:
+        layout = DEFAULT_LAYOUT                       # a rank without persons still knows the standard record
+    widths = set(int(w) for w in counts[:, 1].tolist() if int(w) > 0)
+    if layout is None or len(widths) > 1:             # unusual key set: agree on it explicitly (pickled, slow path)
+        layouts = [None] * world
+        dist.all_gather_object(layouts, layout, group=group)
+        layout = next(l for l in layouts if l is not None)
     fpad = torch.zeros(nmax, width, device=device)
     ipad = torch.zeros(nmax, 3, dtype=torch.int64, device=device)
     if frec.shape[0]:
         fpad[:frec.shape[0]] = frec
         ipad[:irec.shape[0]] = irec
-    fall = torch.zeros(world * nmax, width, device=device)
-    iall = torch.zeros(world * nmax, 3, dtype=torch.int64, device=device)
+    fall = torch.empty(world * nmax, width, device=device)
+    iall = torch.empty(world * nmax, 3, dtype=torch.int64, device=device)
     dist.all_gather_into_tensor(fall, fpad, group=group)
     dist.all_gather_into_tensor(iall, ipad, group=group)
-    keep = torch.cat([torch.arange(r * nmax, r * nmax + int(counts[r, 0])) for r in range(world)]).to(device)
-    res = unpack(fall[keep], iall[keep], layout)
-    if to_numpy:
-        res = {k: v.contiguous().cpu().numpy() for k, v in res.items()}
-    return res
+    ntot = int(counts[:, 0].sum())
+    if not to_numpy:
+        keep = torch.cat([torch.arange(r * nmax, r * nmax + int(counts[r, 0])) for r in range(world)]).to(device)
+        return unpack(fall[keep], iall[keep], layout)
+    # D2H of the valid rows of every rank's slab into cached pinned mirrors, then host-side views
+    fh, ih = _pinned("f", ntot, width, torch.float32), _pinned("i", ntot, 3, torch.int64)
+    row = 0
+    for r in range(world):
+        c = int(counts[r, 0])
+        if c:
+            fh[row:row + c].copy_(fall[r * nmax:r * nmax + c], non_blocking=True)
+            ih[row:row + c].copy_(iall[r * nmax:r * nmax + c], non_blocking=True)
+            row += c
+    if device.type == "cuda":
+        torch.cuda.current_stream().synchronize()
+    return {k: v.numpy() for k, v in unpack(fh[:ntot], ih[:ntot], layout).items()}
+
+
+DEFAULT_LAYOUT = [("cam", (3,)), ("smpl_thetas", (72,)), ("smpl_betas", (10,)), ("center_confs", (1,)), ("cam_trans", (3,)),
+                  ("joints", (71, 3)), ("pj2d_org", (71, 2)), ("verts", (6890, 3))]
+DEFAULT_WIDTH = sum(int(np.prod(s)) for _, s in DEFAULT_LAYOUT)
+_PIN = {}
+
+
+def _pinned(tag, rows, width, dtype):
+    """Grow-only pinned host mirror (valid until the next gather that needs it)."""
+    key = (tag, width, dtype)
+    buf = _PIN.get(key)
+    if buf is None or buf.shape[0] < rows:
+        buf = torch.empty(max(rows, 64) * 2, width, dtype=dtype)
+        if torch.cuda.is_available():
+            buf = buf.pin_memory()
+        _PIN[key] = buf
+    return buf

@@ -16,7 +16,13 @@ __device__ __forceinline__ void umma(uint32_t d, uint64_t a, uint64_t b, uint32_
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
 
-template <int M, int N>
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+template <int M, int N, int ELECT>
 __global__ void __launch_bounds__(128) bench(int issuers, int iters, int tmem_cols, long long* out) {
   extern __shared__ uint8_t raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
@@ -38,7 +44,25 @@ __global__ void __launch_bounds__(128) bench(int issuers, int iters, int tmem_co
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tm = tmem_ptr;
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-  if (lane == 0 && warp < issuers) {
+  if (ELECT == 2 && warp < issuers) {
+    // warp-converged issue loop: every lane computes the (uniform) descriptors, one elected lane issues
+    const uint32_t a0 = smem_u32(smem) + warp * 64, b0 = smem_u32(smem + 20 * 1024);
+    const uint32_t d = tm + warp * N;
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int j = 0; j < 36; ++j) {
+        const int t = j / 4, k = j % 4;
+        const uint64_t ad = make_desc(a0 + ((t / 3) * 10 + t % 3) * 128 + (k & 1) * 32, 1280, 2), bd = make_desc(b0 + k * 32, 1024, 2);
+        if (elect_one()) umma(d, ad, bd, idesc, (it | j) ? 1u : 0u);
+      }
+    }
+    if (elect_one()) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar[warp])) : "memory");
+    uint32_t ok = 0;
+    while (!ok) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(&bar[warp])), "r"(0) : "memory");
+    long long t1 = clock64();
+    if (blockIdx.x == 0 && warp == 0 && lane == 0) *out = t1 - t0;
+  } else if (ELECT != 2 && warp < issuers && (ELECT ? elect_one() : lane == 0)) {
     const uint32_t a0 = smem_u32(smem) + warp * 64, b0 = smem_u32(smem + 20 * 1024);
     const uint32_t d = tm + warp * N;
     long long t0 = clock64();
@@ -58,25 +82,27 @@ __global__ void __launch_bounds__(128) bench(int issuers, int iters, int tmem_co
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(tmem_cols) : "memory");
 }
 
-template <int M, int N>
+template <int M, int N, int ELECT = 0>
 void run(int ctas_per_sm, int issuers) {
   long long* d;
   cudaMalloc(&d, 8);
   const int iters = 200, smem = 64 * 1024;     // 64 KB + alignment: three CTAs fit per SM, we launch 1 or 2 per SM
   const int tmem_cols = 256;
-  cudaFuncSetAttribute(bench<M, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  bench<M, N><<<148 * ctas_per_sm, 128, smem>>>(issuers, 10, tmem_cols, d);
-  bench<M, N><<<148 * ctas_per_sm, 128, smem>>>(issuers, iters, tmem_cols, d);
+  cudaFuncSetAttribute(bench<M, N, ELECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  bench<M, N, ELECT><<<148 * ctas_per_sm, 128, smem>>>(issuers, 10, tmem_cols, d);
+  bench<M, N, ELECT><<<148 * ctas_per_sm, 128, smem>>>(issuers, iters, tmem_cols, d);
   cudaError_t e = cudaDeviceSynchronize();
   long long h = 0;
   cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
   const double clk = (double)h / (iters * 36.0);
-  printf("M=%3d N=%3d  CTAs/SM=%d issuers/CTA=%d : %7.1f clk per MMA per issuer -> %6.0f MAC/clk/SM (peak 4096)  %s\n", M, N, ctas_per_sm,
+  printf("%s M=%3d N=%3d  CTAs/SM=%d issuers/CTA=%d : %7.1f clk per MMA per issuer -> %6.0f MAC/clk/SM (peak 4096)  %s\n", ELECT == 2 ? "warpcv" : (ELECT ? "elect " : "lane0 "), M, N, ctas_per_sm,
          issuers, clk, (double)M * N * 16 * ctas_per_sm * issuers / clk, e == cudaSuccess ? "" : cudaGetErrorString(e));
   cudaFree(d);
 }
 
 int main() {
+  run<128, 32, 2>(1, 1); run<128, 64, 2>(1, 1); run<128, 64, 2>(1, 2); run<128, 128, 2>(1, 1); run<128, 32, 2>(1, 2);
+  run<128, 32, 1>(1, 1); run<128, 64, 1>(1, 1);
   run<128, 32>(1, 1); run<128, 32>(2, 1); run<128, 32>(1, 2); run<128, 32>(2, 2);
   run<128, 64>(1, 1); run<128, 64>(2, 1); run<128, 64>(1, 2); run<128, 64>(2, 2);
   run<128, 128>(1, 1); run<128, 128>(2, 1); run<128, 128>(1, 2);
