@@ -47,6 +47,7 @@ struct ConvParams {
   int relu, pow_channel, out_nchw;
   int in_dtype, out_dtype, res_dtype;
   int input_norm;
+  int debug;   // B200ROMP_TC_DEBUG bit mask (profiling experiments only): 1 = epilogue without global traffic, 2 = no MMAs, 4 = no TMA loads
 };
 
 // ---- epilogue shared by the SIMT and tcgen05 conv kernels ---------------------------------------

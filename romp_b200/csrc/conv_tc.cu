@@ -101,6 +101,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, con
         for (int c = 0; c < Cfg::KCH; ++c) {
           for (int l = 0; l < Cfg::LOADS_PER_CHUNK; ++l) {
             mbar_wait(&empty[stage], phase ^ 1);
+            if (p.debug & 4) { mbar_arrive(&full[stage]); if (++stage == stages) { stage = 0; phase ^= 1; } continue; }
             mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_PAYLOAD);
             const int dy = PER_TAP ? l / KS - Cfg::PAD : -Cfg::PAD;
             const int dx = PER_TAP ? l % KS - Cfg::PAD : -Cfg::PAD;
@@ -139,7 +140,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, con
               for (int k = 0; k < Cfg::CW / 16; ++k) {
                 const uint64_t adesc = make_smem_desc(a_tap + k * 32, Cfg::HW_ * Cfg::ROWB, Cfg::LAYOUT);
                 const uint64_t bdesc = make_smem_desc(b_tap + k * 32, 8 * Cfg::ROWB, Cfg::LAYOUT);
-                umma_bf16(d_tile + (uint32_t)((mma_i % KSPLIT) * NT), adesc, bdesc, Cfg::IDESC, mma_i >= KSPLIT ? 1u : 0u);
+                if (!(p.debug & 2)) umma_bf16(d_tile + (uint32_t)((mma_i % KSPLIT) * NT), adesc, bdesc, Cfg::IDESC, mma_i >= KSPLIT ? 1u : 0u);
                 ++mma_i;
               }
             }

@@ -92,6 +92,7 @@ static int fill_params(b200romp_net* net, const Op& op, int batch, ConvParams* o
   }
   p.relu = d.relu; p.pow_channel = d.pow_channel; p.out_nchw = to.nchw;
   p.in_dtype = ti.dtype; p.out_dtype = to.dtype; p.input_norm = d.input_norm;
+  { static const int dbg = getenv("B200ROMP_TC_DEBUG") ? atoi(getenv("B200ROMP_TC_DEBUG")) : 0; p.debug = dbg; }
   if (!p.in || !p.out) {
     set_error("op uses an unbound tensor (in=%d out=%d)", d.in, d.out);
     return B200ROMP_ESTATE;

@@ -234,7 +234,8 @@ __device__ __forceinline__ void tc_epilogue_loop(const ConvParams& p, uint32_t t
           const int fy = oy * up + dy, fx = ox * up + dx;
           const size_t pix = ((size_t)n * Hf + fy) * Wf + fx;
           const size_t rpix = ((size_t)(p.res_broadcast ? 0 : n) * Hf + fy) * Wf + fx;
-          tc_store32(p, pix, rpix, co0 + c0, v);
+          if (!(p.debug & 1)) tc_store32(p, pix, rpix, co0 + c0, v);
+          else if (v[0] == 123.456f) reinterpret_cast<float*>(p.out)[0] = v[1];   // keep the TMEM loads alive
         }
       }
     }
