@@ -78,7 +78,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, con
     }
     fence_barrier_init();
   }
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + NT) s_bias[threadIdx.x - 64] = p.bias[blockIdx.y * NT + threadIdx.x - 64];
+  if (threadIdx.x >= kFirstEpiWarp * 32 && threadIdx.x < kFirstEpiWarp * 32 + NT)
+    s_bias[threadIdx.x - kFirstEpiWarp * 32] = p.bias[blockIdx.y * NT + threadIdx.x - kFirstEpiWarp * 32];
   if (warp == 1) tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -88,7 +89,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, con
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(b_full, Cfg::B_BYTES);
       const uint8_t* wsrc = wpack + (size_t)blockIdx.y * Cfg::B_BYTES;
       for (int i = 0; i < Cfg::TAPS * Cfg::KCH; ++i)
@@ -111,16 +112,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, con
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (single thread) =====================
-    if (lane == 0) {
+  } else if (warp <= kMmaWarps) {
+    // ===================== MMA issuers: warp w takes the CTA's tiles w-1, w-1+kMmaWarps, ... (one elected thread each) =====================
+    if (elect_one()) {
       mbar_wait(b_full, 0);
       tc_fence_after();
       const uint32_t b_base = smem_u32(sB);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      constexpr int kStagesPerTile = Cfg::KCH * Cfg::LOADS_PER_CHUNK;
+      int it = warp - 1;
+      for (int tile = blockIdx.x + it * gridDim.x; tile < num_tiles; tile += kMmaWarps * gridDim.x, it += kMmaWarps) {
+        int g = it * kStagesPerTile;                 // position of this tile's first stage in the producer's sequence
+        int stage = g % stages;
+        uint32_t phase = (uint32_t)(g / stages) & 1u;
         const int acc = it & (kAccStages - 1);
         mbar_wait(&tmem_empty[acc], ((it / kAccStages) & 1) ^ 1);
         tc_fence_after();

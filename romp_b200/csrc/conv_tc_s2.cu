@@ -76,7 +76,8 @@ conv_tc_s2_kernel(const __grid_constant__ S2Maps maps, const ConvParams p, const
     }
     fence_barrier_init();
   }
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + NT) s_bias[threadIdx.x - 64] = p.bias[blockIdx.y * NT + threadIdx.x - 64];
+  if (threadIdx.x >= kFirstEpiWarp * 32 && threadIdx.x < kFirstEpiWarp * 32 + NT)
+    s_bias[threadIdx.x - kFirstEpiWarp * 32] = p.bias[blockIdx.y * NT + threadIdx.x - kFirstEpiWarp * 32];
   if (warp == 1) tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -85,7 +86,7 @@ conv_tc_s2_kernel(const __grid_constant__ S2Maps maps, const ConvParams p, const
   const int per_frame = tiles_x * tiles_y;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(b_full, Cfg::B_BYTES);
       const uint8_t* wsrc = wpack + (size_t)blockIdx.y * Cfg::B_BYTES;
       for (int i = 0; i < 9 * Cfg::KCH; ++i)
@@ -108,14 +109,16 @@ conv_tc_s2_kernel(const __grid_constant__ S2Maps maps, const ConvParams p, const
         }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
+  } else if (warp <= kMmaWarps) {
+    if (elect_one()) {      // two MMA-issuing warps alternate tiles (see conv_tc.cu)
       mbar_wait(b_full, 0);
       tc_fence_after();
       const uint32_t b_base = smem_u32(sB);
-      int stage = 0, it = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      int it = warp - 1;
+      for (int tile = blockIdx.x + it * gridDim.x; tile < num_tiles; tile += kMmaWarps * gridDim.x, it += kMmaWarps) {
+        int g = it * Cfg::KCH;
+        int stage = g % stages;
+        uint32_t phase = (uint32_t)(g / stages) & 1u;
         const int acc = it & (kAccStages - 1);
         mbar_wait(&tmem_empty[acc], ((it / kAccStages) & 1) ^ 1);
         tc_fence_after();

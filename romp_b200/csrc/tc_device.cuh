@@ -45,6 +45,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -177,7 +182,9 @@ __host__ __device__ constexpr int tc_ksplit(int mmas_per_tile, int nt) {
 }
 __host__ __device__ constexpr int tc_tmem_cols(int cols) { return cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512; }
 constexpr int kEpiWarps = 8;         // two groups of 4 warps, alternating tiles
-constexpr int kTcThreads = 64 + kEpiWarps * 32;
+constexpr int kMmaWarps = 2;         // two MMA-issuing warps alternate tiles: one thread sustains only ~1 tcgen05.mma / 50-75 clk
+constexpr int kFirstEpiWarp = 1 + kMmaWarps;
+constexpr int kTcThreads = (kFirstEpiWarp + kEpiWarps) * 32;
 
 // Epilogue of a persistent tile loop: 2 groups x 4 warps (warps 2..9), group g takes the CTA's tiles g, g+2, ...
 // Each warp owns the TMEM lane quarter (warp id mod 4); thread = one pixel of the 16x8 tile.
@@ -186,7 +193,7 @@ __device__ __forceinline__ void tc_epilogue_loop(const ConvParams& p, uint32_t t
                                                  uint64_t* tmem_empty, const float* s_bias, int tiles_x, int per_frame,
                                                  int num_tiles) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int group = (warp - 2) >> 2;
+  const int group = (warp - kFirstEpiWarp) >> 2;
   const int q = warp & 3;
   const int m = q * 32 + lane;
   const int co0 = blockIdx.y * NT;
