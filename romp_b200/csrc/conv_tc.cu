@@ -86,6 +86,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const int per_frame = tiles_x * tiles_y;
+  const int nrings = stages >= 2 ? kMmaWarps : 1;   // MMA-issuing warps in use = private stage rings
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -94,36 +95,45 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, con
       const uint8_t* wsrc = wpack + (size_t)blockIdx.y * Cfg::B_BYTES;
       for (int i = 0; i < Cfg::TAPS * Cfg::KCH; ++i)
         bulk_copy_g2s(sB + (size_t)i * Cfg::BTILE, wsrc + (size_t)i * Cfg::BTILE, Cfg::BTILE, b_full);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      // Each MMA warp owns a private stage ring (ring r = stages [ring_base(r), ring_base(r) + ring_size(r))): mbarrier
+      // waits only see the phase parity, so a ring must have exactly one in-order consumer (TMA completions of
+      // different stages arrive out of order, a shared ring would alias phases).  Tile i of this CTA goes to ring i & 1.
+      int stage = 0, stage_other = 0;        
+      uint32_t phase = 0, phase_other = 0;   // (stage, phase) of the current tile's ring / of the other ring
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const int n = tile / per_frame, rem = tile % per_frame;
         const int y0 = (rem / tiles_x) * 16, x0 = (rem % tiles_x) * 8;
+        const int ring = nrings == 2 ? (it & 1) : 0, rbase = tc_ring_base(stages, ring), rsize = tc_ring_size(stages, ring);
         for (int c = 0; c < Cfg::KCH; ++c) {
           for (int l = 0; l < Cfg::LOADS_PER_CHUNK; ++l) {
-            mbar_wait(&empty[stage], phase ^ 1);
-            if (p.debug & 4) { mbar_arrive(&full[stage]); if (++stage == stages) { stage = 0; phase ^= 1; } continue; }
-            mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_PAYLOAD);
-            const int dy = PER_TAP ? l / KS - Cfg::PAD : -Cfg::PAD;
-            const int dx = PER_TAP ? l % KS - Cfg::PAD : -Cfg::PAD;
-            tma_load_4d(sA + (size_t)stage * Cfg::STAGE_BYTES, &tmap, &full[stage], c * Cfg::CW, x0 + dx, y0 + dy, n);
-            if (++stage == stages) { stage = 0; phase ^= 1; }
+            const int sidx = rbase + stage;
+            mbar_wait(&empty[sidx], phase ^ 1);
+            if (p.debug & 4) {
+              mbar_arrive(&full[sidx]);
+            } else {
+              mbar_arrive_expect_tx(&full[sidx], Cfg::STAGE_PAYLOAD);
+              const int dy = PER_TAP ? l / KS - Cfg::PAD : -Cfg::PAD;
+              const int dx = PER_TAP ? l % KS - Cfg::PAD : -Cfg::PAD;
+              tma_load_4d(sA + (size_t)sidx * Cfg::STAGE_BYTES, &tmap, &full[sidx], c * Cfg::CW, x0 + dx, y0 + dy, n);
+            }
+            if (++stage == rsize) { stage = 0; phase ^= 1; }
           }
         }
+        if (nrings == 2) { const int ts = stage; stage = stage_other; stage_other = ts; const uint32_t tp = phase; phase = phase_other; phase_other = tp; }
       }
     }
   } else if (warp <= kMmaWarps) {
     // ===================== MMA issuers: warp w takes the CTA's tiles w-1, w-1+kMmaWarps, ... (one elected thread each) =====================
-    if (elect_one()) {
+    if (warp <= nrings && elect_one()) {
       mbar_wait(b_full, 0);
       tc_fence_after();
       const uint32_t b_base = smem_u32(sB);
-      constexpr int kStagesPerTile = Cfg::KCH * Cfg::LOADS_PER_CHUNK;
+      const int rbase = tc_ring_base(stages, warp - 1), rsize = tc_ring_size(stages, warp - 1);   // this warp's private ring
+      int stage = 0;
+      uint32_t phase = 0;
       int it = warp - 1;
-      for (int tile = blockIdx.x + it * gridDim.x; tile < num_tiles; tile += kMmaWarps * gridDim.x, it += kMmaWarps) {
-        int g = it * kStagesPerTile;                 // position of this tile's first stage in the producer's sequence
-        int stage = g % stages;
-        uint32_t phase = (uint32_t)(g / stages) & 1u;
+      for (int tile = blockIdx.x + it * gridDim.x; tile < num_tiles; tile += nrings * gridDim.x, it += nrings) {
         const int acc = it & (kAccStages - 1);
         mbar_wait(&tmem_empty[acc], ((it / kAccStages) & 1) ^ 1);
         tc_fence_after();
@@ -131,9 +141,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, con
         int mma_i = 0;
         for (int c = 0; c < Cfg::KCH; ++c) {
           for (int l = 0; l < Cfg::LOADS_PER_CHUNK; ++l) {
-            mbar_wait(&full[stage], phase);
+            const int sidx = rbase + stage;
+            mbar_wait(&full[sidx], phase);
             tc_fence_after();
-            const uint32_t a_base = smem_u32(sA + (size_t)stage * Cfg::STAGE_BYTES);
+            const uint32_t a_base = smem_u32(sA + (size_t)sidx * Cfg::STAGE_BYTES);
             const int t_lo = PER_TAP ? l : 0, t_hi = PER_TAP ? l + 1 : Cfg::TAPS;
             for (int t = t_lo; t < t_hi; ++t) {
               const int r = t / KS, s = t % KS;
@@ -147,8 +158,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, con
                 ++mma_i;
               }
             }
-            umma_commit(&empty[stage]);          // smem stage reusable once these MMAs retire
-            if (++stage == stages) { stage = 0; phase ^= 1; }
+            umma_commit(&empty[sidx]);           // smem stage reusable once these MMAs retire
+            if (++stage == rsize) { stage = 0; phase ^= 1; }
           }
         }
         umma_commit(&tmem_full[acc]);            // accumulator complete -> epilogue
@@ -288,7 +299,7 @@ int tc_conv_prepare(const ConvParams& p, int ksize, int stride, const float* w_o
     return B200ROMP_EINVAL;
   }
   int stages = (budget - bbytes(nt)) / stage_bytes;
-  stages = std::min(stages, per_tap ? 12 : 6);
+  stages = std::min(stages, per_tap ? 12 : 8);   // split into two rings (one per MMA warp)
   plan->kind = ksize * 10 + (per_tap ? 1 : 0);
   plan->cin = p.cin; plan->cout = p.cout; plan->nt = nt; plan->stages = stages;
   plan->grid_y = (p.cout + nt - 1) / nt;

@@ -84,6 +84,7 @@ conv_tc_s2_kernel(const __grid_constant__ S2Maps maps, const ConvParams p, const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const int per_frame = tiles_x * tiles_y;
+  const int nrings = stages >= 2 ? kMmaWarps : 1;   // MMA-issuing warps in use = private stage rings
 
   if (warp == 0) {
     if (elect_one()) {
@@ -91,43 +92,48 @@ conv_tc_s2_kernel(const __grid_constant__ S2Maps maps, const ConvParams p, const
       const uint8_t* wsrc = wpack + (size_t)blockIdx.y * Cfg::B_BYTES;
       for (int i = 0; i < 9 * Cfg::KCH; ++i)
         bulk_copy_g2s(sB + (size_t)i * Cfg::BTILE, wsrc + (size_t)i * Cfg::BTILE, Cfg::BTILE, b_full);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int stage = 0, stage_other = 0;                  // one private stage ring per MMA warp (see conv_tc.cu)
+      uint32_t phase = 0, phase_other = 0;   // (stage, phase) of the current tile's ring / of the other ring
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const int n = tile / per_frame, rem = tile % per_frame;
         const int y0 = (rem / tiles_x) * 16, x0 = (rem % tiles_x) * 8;      // output coordinates
+        const int ring = nrings == 2 ? (it & 1) : 0, rbase = tc_ring_base(stages, ring), rsize = tc_ring_size(stages, ring);
         for (int c = 0; c < Cfg::KCH; ++c) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_PAYLOAD);
-          uint8_t* dst = sA + (size_t)stage * Cfg::STAGE_BYTES;
+          const int sidx = rbase + stage;
+          mbar_wait(&empty[sidx], phase ^ 1);
+          mbar_arrive_expect_tx(&full[sidx], Cfg::STAGE_PAYLOAD);
+          uint8_t* dst = sA + (size_t)sidx * Cfg::STAGE_BYTES;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int ph = i < 2 ? 1 : 0, pw = (i & 1) ? 0 : 1;
-            tma_load_5d(dst + Cfg::SUB_OFF(i), &maps.m[i], &full[stage], pw * CIN + c * Cfg::CW, x0 - pw, ph, y0 - ph, n);
+            tma_load_5d(dst + Cfg::SUB_OFF(i), &maps.m[i], &full[sidx], pw * CIN + c * Cfg::CW, x0 - pw, ph, y0 - ph, n);
           }
-          if (++stage == stages) { stage = 0; phase ^= 1; }
+          if (++stage == rsize) { stage = 0; phase ^= 1; }
         }
+        if (nrings == 2) { const int ts = stage; stage = stage_other; stage_other = ts; const uint32_t tp = phase; phase = phase_other; phase_other = tp; }
       }
     }
   } else if (warp <= kMmaWarps) {
-    if (elect_one()) {      // two MMA-issuing warps alternate tiles (see conv_tc.cu)
+    if (warp <= nrings && elect_one()) {      // two MMA-issuing warps alternate tiles (see conv_tc.cu)
       mbar_wait(b_full, 0);
       tc_fence_after();
       const uint32_t b_base = smem_u32(sB);
+      const int rbase = tc_ring_base(stages, warp - 1), rsize = tc_ring_size(stages, warp - 1);
+      int stage = 0;
+      uint32_t phase = 0;
       int it = warp - 1;
-      for (int tile = blockIdx.x + it * gridDim.x; tile < num_tiles; tile += kMmaWarps * gridDim.x, it += kMmaWarps) {
-        int g = it * Cfg::KCH;
-        int stage = g % stages;
-        uint32_t phase = (uint32_t)(g / stages) & 1u;
+      for (int tile = blockIdx.x + it * gridDim.x; tile < num_tiles; tile += nrings * gridDim.x, it += nrings) {
         const int acc = it & (kAccStages - 1);
         mbar_wait(&tmem_empty[acc], ((it / kAccStages) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tile = tmem_base + (uint32_t)(acc * KSPLIT * NT);
         int mma_i = 0;
         for (int c = 0; c < Cfg::KCH; ++c) {
-          mbar_wait(&full[stage], phase);
+          const int sidx = rbase + stage;
+          mbar_wait(&full[sidx], phase);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(sA + (size_t)stage * Cfg::STAGE_BYTES);
+          const uint32_t a_base = smem_u32(sA + (size_t)sidx * Cfg::STAGE_BYTES);
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
             const int r = t / 3, s = t % 3;
@@ -143,8 +149,8 @@ conv_tc_s2_kernel(const __grid_constant__ S2Maps maps, const ConvParams p, const
               ++mma_i;
             }
           }
-          umma_commit(&empty[stage]);
-          if (++stage == stages) { stage = 0; phase ^= 1; }
+          umma_commit(&empty[sidx]);
+          if (++stage == rsize) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[acc]);
       }

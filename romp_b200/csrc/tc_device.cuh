@@ -115,7 +115,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t sbo_b
 
 // 32 consecutive output channels of one full-resolution pixel: residual add, ReLU, dtype conversion, all with
 // 16-byte vector accesses; every load is issued before the first use so one thread keeps 4-8 requests in flight.
-__device__ __forceinline__ void tc_store32(const ConvParams& p, size_t pix, size_t rpix, int co, const float (&acc)[32]) {
+// `pre` (optional) holds the 4 x 16 B of a bf16 residual that the caller fetched before the accumulator was ready.
+__device__ __forceinline__ void tc_store32(const ConvParams& p, size_t pix, size_t rpix, int co, const float (&acc)[32],
+                                           const uint4* pre = nullptr) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = acc[j];
@@ -123,8 +125,13 @@ __device__ __forceinline__ void tc_store32(const ConvParams& p, size_t pix, size
     if (p.res_dtype == B200ROMP_BF16) {
       const uint4* r = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res) + rpix * p.res_C + p.res_c_off + co);
       uint4 t[4];
+      if (pre != nullptr) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) t[i] = r[i];
+        for (int i = 0; i < 4; ++i) t[i] = pre[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t[i] = r[i];
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t[i]);
@@ -184,6 +191,10 @@ __host__ __device__ constexpr int tc_tmem_cols(int cols) { return cols <= 32 ? 3
 constexpr int kEpiWarps = 8;         // two groups of 4 warps, alternating tiles
 constexpr int kMmaWarps = 2;         // two MMA-issuing warps alternate tiles: one thread sustains only ~1 tcgen05.mma / 50-75 clk
 constexpr int kFirstEpiWarp = 1 + kMmaWarps;
+// the smem stages are split into one private ring per MMA warp: ring 0 gets the larger half
+// (a single stage cannot be split: then only the first MMA warp works and owns it)
+__host__ __device__ constexpr int tc_ring_size(int stages, int ring) { return stages < 2 ? stages : (stages + 1 - ring) / 2; }
+__host__ __device__ constexpr int tc_ring_base(int stages, int ring) { return ring ? (stages + 1) / 2 : 0; }
 constexpr int kTcThreads = (kFirstEpiWarp + kEpiWarps) * 32;
 
 // Epilogue of a persistent tile loop: 2 groups x 4 warps (warps 2..9), group g takes the CTA's tiles g, g+2, ...
@@ -205,6 +216,15 @@ __device__ __forceinline__ void tc_epilogue_loop(const ConvParams& p, uint32_t t
     const int acc = it & (ACC - 1);
     const int n = tile / per_frame, rem = tile % per_frame;
     const int oy = (rem / tiles_x) * 16 + (m >> 3), ox = (rem % tiles_x) * 8 + (m & 7);
+    // the residual does not depend on the accumulator: fetch it while the MMAs of this tile are still running
+    uint4 pre[NT / 8];
+    const bool prefetch = p.res != nullptr && p.res_dtype == B200ROMP_BF16 && up == 1 && !p.out_nchw && !(p.debug & 1);
+    if (prefetch) {
+      const size_t rpix0 = ((size_t)(p.res_broadcast ? 0 : n) * Hf + oy) * Wf + ox;
+      const uint4* r = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res) + rpix0 * p.res_C + p.res_c_off + co0);
+#pragma unroll
+      for (int i = 0; i < NT / 8; ++i) pre[i] = r[i];
+    }
     mbar_wait(&tmem_full[acc], (it / ACC) & 1);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * KSPLIT * NT);
@@ -241,7 +261,8 @@ __device__ __forceinline__ void tc_epilogue_loop(const ConvParams& p, uint32_t t
           const int fy = oy * up + dy, fx = ox * up + dx;
           const size_t pix = ((size_t)n * Hf + fy) * Wf + fx;
           const size_t rpix = ((size_t)(p.res_broadcast ? 0 : n) * Hf + fy) * Wf + fx;
-          if (!(p.debug & 1)) tc_store32(p, pix, rpix, co0 + c0, v);
+          if (prefetch) tc_store32(p, pix, rpix, co0 + c0, v, pre + c0 / 8);
+          else if (!(p.debug & 1)) tc_store32(p, pix, rpix, co0 + c0, v);
           else if (v[0] == 123.456f) reinterpret_cast<float*>(p.out)[0] = v[1];   // keep the TMEM loads alive
         }
       }

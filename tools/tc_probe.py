@@ -48,6 +48,8 @@ PERF = [
     ("perf_s2_c64_128to64", 3, 64, 64, 128, 128, 64, 1, 0, 1, 0, 1, 2),
     ("perf_s2_c32_n64_128to64", 3, 32, 64, 128, 128, 64, 1, 0, 1, 0, 1, 2),
     ("perf_k1_c256_n64_128", 1, 256, 64, 128, 128, 64, 1, 0, 1, 0, 1),
+    ("perf_s2_c256_n256_32to16", 3, 256, 256, 32, 32, 64, 1, 0, 1, 0, 1, 2),
+    ("perf_s2_c128_n128_64to32", 3, 128, 128, 64, 64, 64, 1, 0, 1, 0, 1, 2),
 ]
 
 
