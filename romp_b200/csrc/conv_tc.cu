@@ -49,20 +49,22 @@ struct TcCfg {
 
 template <int KS, int CIN, int NT, bool PER_TAP, int KSPLIT>
 __global__ void __launch_bounds__(kTcThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, const uint8_t* __restrict__ wpack,
-               int tiles_x, int tiles_y, int num_tiles, int stages) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcEpiMaps epi_maps, const ConvParams p,
+               const uint8_t* __restrict__ wpack, int tiles_x, int tiles_y, int num_tiles, int stages, int tma_epi) {
   using Cfg = TcCfg<KS, CIN, NT, PER_TAP, KSPLIT>;
   constexpr int kAccStages = Cfg::ACC;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sB = smem;
   uint8_t* sA = smem + Cfg::B_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sA + (size_t)stages * Cfg::STAGE_BYTES);
+  uint8_t* epi_smem = sA + (size_t)stages * Cfg::STAGE_BYTES;       // TMA-epilogue staging tiles (1024 B aligned), if any
+  uint64_t* full = reinterpret_cast<uint64_t*>(epi_smem + (tma_epi ? kEpiWarps * tc_epi_stage_bytes(NT) : 0));
   uint64_t* empty = full + stages;
   uint64_t* b_full = empty + stages;
   uint64_t* tmem_full = b_full + 1;
   uint64_t* tmem_empty = tmem_full + kAccStages;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + kAccStages);
+  uint64_t* res_bar = tmem_empty + kAccStages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + kEpiWarps);
   float* s_bias = reinterpret_cast<float*>(tmem_ptr + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -76,6 +78,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, con
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 4);
     }
+    for (int i = 0; i < kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (threadIdx.x >= kFirstEpiWarp * 32 && threadIdx.x < kFirstEpiWarp * 32 + NT)
@@ -165,6 +168,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, con
         umma_commit(&tmem_full[acc]);            // accumulator complete -> epilogue
       }
     }
+  } else if (KSPLIT == 1 && tma_epi) {
+    tc_epilogue_loop_tma<NT>(p, epi_maps, tma_epi, epi_smem, res_bar, tmem_base, tmem_full, tmem_empty, s_bias, tiles_x, per_frame,
+                             num_tiles);
   } else {
     tc_epilogue_loop<NT, KSPLIT>(p, tmem_base, tmem_full, tmem_empty, s_bias, tiles_x, per_frame, num_tiles);
   }
@@ -219,7 +225,7 @@ int tc_pack_weights(const float* w_oihw, int cin, int cout, int taps, int nt, vo
 
 std::string TcConvPlan::describe() const {
   char buf[96];
-  snprintf(buf, sizeof(buf), " [tc k%d v%d nt%d grid %dx%d smem %d stages %d]", kind / 10, kind % 10, nt, grid_x, grid_y, smem_bytes, stages);
+  snprintf(buf, sizeof(buf), " [tc k%d v%d nt%d grid %dx%d smem %d stages %d epi%d]", kind / 10, kind % 10, nt, grid_x, grid_y, smem_bytes, stages, tma_epi);
   return buf;
 }
 
@@ -250,11 +256,13 @@ static int launch_inst(const TcConvPlan& plan, const ConvParams& p, cudaStream_t
   }
   CUtensorMap tm;
   memcpy(&tm, plan.tmap_in, sizeof(tm));
+  TcEpiMaps em;
+  memcpy(&em, plan.tmap_epi, sizeof(em));
   const int tiles_x = p.Wout / 8, tiles_y = p.Hout / 16;
   const int num_tiles = tiles_x * tiles_y * p.B;
   dim3 grid(std::min(plan.grid_x, num_tiles), plan.grid_y);
-  kern<<<grid, kTcThreads, plan.smem_bytes, stream>>>(tm, p, reinterpret_cast<const uint8_t*>(plan.d_wpack), tiles_x, tiles_y,
-                                               num_tiles, plan.stages);
+  kern<<<grid, kTcThreads, plan.smem_bytes, stream>>>(tm, em, p, reinterpret_cast<const uint8_t*>(plan.d_wpack), tiles_x, tiles_y,
+                                               num_tiles, plan.stages, KSPLIT == 1 ? plan.tma_epi : 0);
   B2R_CUDA_OK(cudaGetLastError());
   return B200ROMP_OK;
 }
@@ -275,9 +283,44 @@ static int dispatch(const TcConvPlan& plan, const ConvParams& p, cudaStream_t st
   return B200ROMP_EINVAL;
 }
 
-int tc_conv_prepare(const ConvParams& p, int ksize, int stride, const float* w_oihw, int sm_count, TcConvPlan* plan,
+// TMA epilogue eligibility + tensor maps over the output / residual tensors: dims (C, W, H, N), box (NT, 8, 4, 1) = the
+// 32 pixels one epilogue warp owns, swizzle matching tc_epi_chunk().  Returns 0 when the direct epilogue must be used.
+int tc_epi_prepare(const ConvParams& p, int nt, bool ptrs_final, TcConvPlan* plan) {
+  plan->tma_epi = 0;
+  const char* e = getenv("B200ROMP_TC_NO_TMA_EPI");
+  if (e && e[0] == '1') return 0;
+  if (!ptrs_final || plan->ksplit != 1 || p.out_dtype != B200ROMP_BF16 || p.out_nchw || p.up != 1 || p.pow_channel >= 0) return 0;
+  if (p.cout % nt != 0 || (reinterpret_cast<uintptr_t>(p.out) & 15) != 0) return 0;
+  const bool res_tma = p.res != nullptr;
+  if (res_tma && (p.res_dtype != B200ROMP_BF16 || p.res_broadcast || (reinterpret_cast<uintptr_t>(p.res) & 15) != 0)) return 0;
+  PFN_encodeTiled encode = tc_get_encode();
+  if (!encode) return 0;
+  auto make = [&](const void* base, int C, unsigned char* dst) -> bool {
+    const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)p.Wout, (cuuint64_t)p.Hout, (cuuint64_t)p.B};
+    const cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)p.Wout * C * 2, (cuuint64_t)p.Hout * p.Wout * C * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)nt, 8, 4, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUtensorMap tm;
+    CUresult cr = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, nt == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return false;
+    memcpy(dst, &tm, sizeof(tm));
+    return true;
+  };
+  if (!make(p.out, p.out_C, plan->tmap_epi[0])) return 0;
+  if (res_tma) {
+    if (!make(p.res, p.res_C, plan->tmap_epi[1])) return 0;
+  } else {
+    memcpy(plan->tmap_epi[1], plan->tmap_epi[0], 128);
+  }
+  plan->tma_epi = kTmaEpiOut | (res_tma ? kTmaEpiRes : 0);
+  return plan->tma_epi;
+}
+
+int tc_conv_prepare(const ConvParams& p, int ksize, int stride, const float* w_oihw, int sm_count, bool ptrs_final, TcConvPlan* plan,
                     std::vector<void*>* allocs) {
-  if (stride == 2) return tc_s2_prepare(p, w_oihw, sm_count, plan, allocs);
+  if (stride == 2) return tc_s2_prepare(p, w_oihw, sm_count, ptrs_final, plan, allocs);
   PFN_encodeTiled encode = tc_get_encode();
   if (!encode) {
     set_error("conv_tc: cuTensorMapEncodeTiled is unavailable");
@@ -298,13 +341,19 @@ int tc_conv_prepare(const ConvParams& p, int ksize, int stride, const float* w_o
     set_error("conv_tc: k%d cin%d does not fit shared memory", ksize, p.cin);
     return B200ROMP_EINVAL;
   }
-  int stages = (budget - bbytes(nt)) / stage_bytes;
+  // TMA epilogue: needs kEpiWarps staging tiles next to >= 2 stages
+  int epi_bytes = 0;
+  if (tc_epi_prepare(p, nt, ptrs_final, plan)) {
+    epi_bytes = kEpiWarps * tc_epi_stage_bytes(nt);
+    if (bbytes(nt) + 2 * stage_bytes + epi_bytes > budget) { plan->tma_epi = 0; epi_bytes = 0; }
+  }
+  int stages = (budget - bbytes(nt) - epi_bytes) / stage_bytes;
   stages = std::min(stages, per_tap ? 12 : 8);   // split into two rings (one per MMA warp)
   plan->kind = ksize * 10 + (per_tap ? 1 : 0);
   plan->cin = p.cin; plan->cout = p.cout; plan->nt = nt; plan->stages = stages;
   plan->grid_y = (p.cout + nt - 1) / nt;
   plan->grid_x = std::max(1, sm_count / plan->grid_y);
-  plan->smem_bytes = bbytes(nt) + stages * stage_bytes + 1024 + 1024;
+  plan->smem_bytes = bbytes(nt) + stages * stage_bytes + epi_bytes + 1024 + 1024;
   int rcw = tc_pack_weights(w_oihw, p.cin, p.cout, taps, nt, &plan->d_wpack, allocs);
   if (rcw) return rcw;
   // ---- tensor map over the NHWC input: dims (C slice, W, H, N), halo box, OOB -> zeros

@@ -16,13 +16,16 @@ struct TcConvPlan {
   void* d_wpack = nullptr;      // weights pre-arranged as the shared-memory image (bf16, swizzled)
   alignas(64) unsigned char tmap_in[128];   // CUtensorMap for the NHWC input tensor
   alignas(64) unsigned char tmap_s2[4][128];  // stride-2: one map per input parity (ph,pw)
+  alignas(64) unsigned char tmap_epi[2][128]; // TMA epilogue: output / residual tensor (box NT x 8 x 4 x 1)
+  int tma_epi = 0;              // bit 0: output through a TMA store, bit 1: residual through a TMA load
   std::string describe() const;
 };
 
 // true when (shape, dtypes, flags) can run on the tcgen05 engine
 bool tc_conv_supported(const ConvParams& p, int ksize, int stride);
 // packs weights, builds tensor maps, picks the tiling; device allocations are appended to `allocs`
-int tc_conv_prepare(const ConvParams& p, int ksize, int stride, const float* w_oihw, int sm_count, TcConvPlan* plan,
+// ptrs_final: the output / residual device pointers in `p` are the ones every launch will use (internal tensors)
+int tc_conv_prepare(const ConvParams& p, int ksize, int stride, const float* w_oihw, int sm_count, bool ptrs_final, TcConvPlan* plan,
                     std::vector<void*>* allocs);
 int tc_conv_launch(const TcConvPlan& plan, const ConvParams& p, cudaStream_t stream);
 

@@ -47,20 +47,22 @@ struct S2Maps {
 
 template <int CIN, int NT, int KSPLIT>
 __global__ void __launch_bounds__(kTcThreads, 1)
-conv_tc_s2_kernel(const __grid_constant__ S2Maps maps, const ConvParams p, const uint8_t* __restrict__ wpack, int tiles_x,
-                  int tiles_y, int num_tiles, int stages) {
+conv_tc_s2_kernel(const __grid_constant__ S2Maps maps, const __grid_constant__ TcEpiMaps epi_maps, const ConvParams p,
+                  const uint8_t* __restrict__ wpack, int tiles_x, int tiles_y, int num_tiles, int stages, int tma_epi) {
   using Cfg = S2Cfg<CIN, NT, KSPLIT>;
   constexpr int kAccStages = Cfg::ACC;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sB = smem;
   uint8_t* sA = smem + Cfg::B_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sA + (size_t)stages * Cfg::STAGE_BYTES);
+  uint8_t* epi_smem = sA + (size_t)stages * Cfg::STAGE_BYTES;       // TMA-epilogue staging tiles, if any
+  uint64_t* full = reinterpret_cast<uint64_t*>(epi_smem + (tma_epi ? kEpiWarps * tc_epi_stage_bytes(NT) : 0));
   uint64_t* empty = full + stages;
   uint64_t* b_full = empty + stages;
   uint64_t* tmem_full = b_full + 1;
   uint64_t* tmem_empty = tmem_full + kAccStages;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + kAccStages);
+  uint64_t* res_bar = tmem_empty + kAccStages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + kEpiWarps);
   float* s_bias = reinterpret_cast<float*>(tmem_ptr + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -74,6 +76,7 @@ conv_tc_s2_kernel(const __grid_constant__ S2Maps maps, const ConvParams p, const
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 4);
     }
+    for (int i = 0; i < kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (threadIdx.x >= kFirstEpiWarp * 32 && threadIdx.x < kFirstEpiWarp * 32 + NT)
@@ -155,6 +158,9 @@ conv_tc_s2_kernel(const __grid_constant__ S2Maps maps, const ConvParams p, const
         umma_commit(&tmem_full[acc]);
       }
     }
+  } else if (KSPLIT == 1 && tma_epi) {
+    tc_epilogue_loop_tma<NT>(p, epi_maps, tma_epi, epi_smem, res_bar, tmem_base, tmem_full, tmem_empty, s_bias, tiles_x, per_frame,
+                             num_tiles);
   } else {
     tc_epilogue_loop<NT, KSPLIT>(p, tmem_base, tmem_full, tmem_empty, s_bias, tiles_x, per_frame, num_tiles);
   }
@@ -189,11 +195,13 @@ static int s2_inst(const TcConvPlan& plan, const ConvParams& p, cudaStream_t str
   }
   S2Maps maps;
   memcpy(&maps, plan.tmap_s2, sizeof(maps));
+  TcEpiMaps em;
+  memcpy(&em, plan.tmap_epi, sizeof(em));
   const int tiles_x = p.Wout / 8, tiles_y = p.Hout / 16;
   const int num_tiles = tiles_x * tiles_y * p.B;
   dim3 grid(std::min(plan.grid_x, num_tiles), plan.grid_y);
-  kern<<<grid, kTcThreads, plan.smem_bytes, stream>>>(maps, p, reinterpret_cast<const uint8_t*>(plan.d_wpack), tiles_x, tiles_y,
-                                                      num_tiles, plan.stages);
+  kern<<<grid, kTcThreads, plan.smem_bytes, stream>>>(maps, em, p, reinterpret_cast<const uint8_t*>(plan.d_wpack), tiles_x, tiles_y,
+                                                      num_tiles, plan.stages, KSPLIT == 1 ? plan.tma_epi : 0);
   B2R_CUDA_OK(cudaGetLastError());
   return B200ROMP_OK;
 }
@@ -210,7 +218,7 @@ static int s2_dispatch(const TcConvPlan& plan, const ConvParams& p, cudaStream_t
   return B200ROMP_EINVAL;
 }
 
-int tc_s2_prepare(const ConvParams& p, const float* w_oihw, int sm_count, TcConvPlan* plan, std::vector<void*>* allocs) {
+int tc_s2_prepare(const ConvParams& p, const float* w_oihw, int sm_count, bool ptrs_final, TcConvPlan* plan, std::vector<void*>* allocs) {
   PFN_encodeTiled encode = tc_get_encode();
   if (!encode) {
     set_error("conv_tc_s2: cuTensorMapEncodeTiled is unavailable");
@@ -228,13 +236,20 @@ int tc_s2_prepare(const ConvParams& p, const float* w_oihw, int sm_count, TcConv
     set_error("conv_tc_s2: cin%d does not fit shared memory", p.cin);
     return B200ROMP_EINVAL;
   }
-  plan->stages = std::min(4, (budget - bbytes(nt)) / stage_bytes);
-  plan->kind = 32;
   { const char* e = getenv("B200ROMP_TC_KSPLIT"); plan->ksplit = (e && e[0] == '4') ? 0 : 1; }   /* K-split measured slower: off by default */
+  // TMA epilogue only where it does not cost the second pipeline stage
+  int epi_bytes = 0;
+  if (tc_epi_prepare(p, nt, ptrs_final, plan)) {
+    epi_bytes = kEpiWarps * tc_epi_stage_bytes(nt);
+    const int without = (budget - bbytes(nt)) / stage_bytes, with = (budget - bbytes(nt) - epi_bytes) / stage_bytes;
+    if (with < 1 || (with < 2 && without >= 2)) { plan->tma_epi = 0; epi_bytes = 0; }
+  }
+  plan->stages = std::min(4, (budget - bbytes(nt) - epi_bytes) / stage_bytes);
+  plan->kind = 32;
   plan->cin = p.cin; plan->cout = p.cout; plan->nt = nt;
   plan->grid_y = p.cout / nt;
   plan->grid_x = std::max(1, sm_count / plan->grid_y);
-  plan->smem_bytes = bbytes(nt) + plan->stages * stage_bytes + 2048;
+  plan->smem_bytes = bbytes(nt) + plan->stages * stage_bytes + epi_bytes + 2048;
   int rc = tc_pack_weights(w_oihw, p.cin, p.cout, 9, nt, &plan->d_wpack, allocs);
   if (rc) return rc;
   const cuuint64_t C = (cuuint64_t)p.in_C;

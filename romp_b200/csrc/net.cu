@@ -304,7 +304,8 @@ int b200romp_net_finalize(b200romp_net* net, int max_batch) {
       if (ext_out_unbound) net->tensors[op.d.out].ptr = nullptr;
       if (params_ok &&
           tc_conv_supported(p, op.d.ksize, op.d.stride)) {
-        rc = tc_conv_prepare(p, op.d.ksize, op.d.stride, op.w_host.data(), net->sm_count, &op.tc, &net->device_allocs);
+        const bool ptrs_final = !to.external && (op.d.res < 0 || !net->tensors[op.d.res].external);
+        rc = tc_conv_prepare(p, op.d.ksize, op.d.stride, op.w_host.data(), net->sm_count, ptrs_final, &op.tc, &net->device_allocs);
         if (rc == B200ROMP_OK) op.engine = B200ROMP_ENGINE_TCGEN05;
         else if (op.d.engine == B200ROMP_ENGINE_TCGEN05) return rc;
       } else if (op.d.engine == B200ROMP_ENGINE_TCGEN05) {

@@ -61,6 +61,15 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// tensor store shared -> global (bulk async-group completion)
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
@@ -115,9 +124,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t sbo_b
 
 // 32 consecutive output channels of one full-resolution pixel: residual add, ReLU, dtype conversion, all with
 // 16-byte vector accesses; every load is issued before the first use so one thread keeps 4-8 requests in flight.
-// `pre` (optional) holds the 4 x 16 B of a bf16 residual that the caller fetched before the accumulator was ready.
-__device__ __forceinline__ void tc_store32(const ConvParams& p, size_t pix, size_t rpix, int co, const float (&acc)[32],
-                                           const uint4* pre = nullptr) {
+__device__ __forceinline__ void tc_store32(const ConvParams& p, size_t pix, size_t rpix, int co, const float (&acc)[32]) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = acc[j];
@@ -125,13 +132,8 @@ __device__ __forceinline__ void tc_store32(const ConvParams& p, size_t pix, size
     if (p.res_dtype == B200ROMP_BF16) {
       const uint4* r = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res) + rpix * p.res_C + p.res_c_off + co);
       uint4 t[4];
-      if (pre != nullptr) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) t[i] = pre[i];
-      } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) t[i] = r[i];
-      }
+      for (int i = 0; i < 4; ++i) t[i] = r[i];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t[i]);
@@ -216,15 +218,6 @@ __device__ __forceinline__ void tc_epilogue_loop(const ConvParams& p, uint32_t t
     const int acc = it & (ACC - 1);
     const int n = tile / per_frame, rem = tile % per_frame;
     const int oy = (rem / tiles_x) * 16 + (m >> 3), ox = (rem % tiles_x) * 8 + (m & 7);
-    // the residual does not depend on the accumulator: fetch it while the MMAs of this tile are still running
-    uint4 pre[NT / 8];
-    const bool prefetch = p.res != nullptr && p.res_dtype == B200ROMP_BF16 && up == 1 && !p.out_nchw && !(p.debug & 1);
-    if (prefetch) {
-      const size_t rpix0 = ((size_t)(p.res_broadcast ? 0 : n) * Hf + oy) * Wf + ox;
-      const uint4* r = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res) + rpix0 * p.res_C + p.res_c_off + co0);
-#pragma unroll
-      for (int i = 0; i < NT / 8; ++i) pre[i] = r[i];
-    }
     mbar_wait(&tmem_full[acc], (it / ACC) & 1);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * KSPLIT * NT);
@@ -261,8 +254,7 @@ __device__ __forceinline__ void tc_epilogue_loop(const ConvParams& p, uint32_t t
           const int fy = oy * up + dy, fx = ox * up + dx;
           const size_t pix = ((size_t)n * Hf + fy) * Wf + fx;
           const size_t rpix = ((size_t)(p.res_broadcast ? 0 : n) * Hf + fy) * Wf + fx;
-          if (prefetch) tc_store32(p, pix, rpix, co0 + c0, v, pre + c0 / 8);
-          else if (!(p.debug & 1)) tc_store32(p, pix, rpix, co0 + c0, v);
+          if (!(p.debug & 1)) tc_store32(p, pix, rpix, co0 + c0, v);
           else if (v[0] == 123.456f) reinterpret_cast<float*>(p.out)[0] = v[1];   // keep the TMEM loads alive
         }
       }
@@ -273,15 +265,125 @@ __device__ __forceinline__ void tc_epilogue_loop(const ConvParams& p, uint32_t t
   }
 }
 
+// ---- TMA epilogue ---------------------------------------------------------------------------------
+// The direct epilogue above has thread = pixel, so one warp-wide 16 B access touches 32 different 128 B lines (32 L1
+// wavefronts); measured, that traffic costs as much as the MMAs of a tile.  For the common case (bf16 NHWC output at the
+// conv resolution, optional bf16 residual of the same shape) each epilogue warp instead owns an NT x 32-pixel staging
+// tile in shared memory (TMA swizzle pattern, conflict-free for row-per-thread 16 B accesses): the residual box arrives
+// by a TMA tensor load issued before the accumulator is awaited, every thread finishes its pixel in place, and one
+// TMA tensor store writes the box (4 rows x 8 pixels x NT channels) with full-line transactions.
+struct TcEpiMaps {
+  CUtensorMap out, res;
+};
+constexpr int kTmaEpiOut = 1, kTmaEpiRes = 2;
+__host__ __device__ constexpr int tc_epi_stage_bytes(int nt) { return 32 * nt * 2; }   // per epilogue warp
+
+template <int NT>
+__device__ __forceinline__ uint4* tc_epi_chunk(uint8_t* stg, int row, int chunk) {
+  // 16 B chunk `chunk` of pixel row `row`: SWIZZLE_128B (NT = 64, 128 B rows) or SWIZZLE_64B (NT = 32, 64 B rows)
+  const int sw = NT == 64 ? (chunk ^ (row & 7)) : (chunk ^ ((row >> 1) & 3));
+  return reinterpret_cast<uint4*>(stg + row * (NT * 2) + sw * 16);
+}
+
+template <int NT>
+__device__ __forceinline__ void tc_epilogue_loop_tma(const ConvParams& p, const TcEpiMaps& maps, int tma_epi, uint8_t* epi_smem,
+                                                     uint64_t* res_bar, uint32_t tmem_base, uint64_t* tmem_full,
+                                                     uint64_t* tmem_empty, const float* s_bias, int tiles_x, int per_frame,
+                                                     int num_tiles) {
+  static_assert(NT == 32 || NT == 64, "staging layout");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ew = warp - kFirstEpiWarp;
+  const int group = ew >> 2;
+  const int q = warp & 3;
+  const int co0 = blockIdx.y * NT;
+  const bool has_res = (tma_epi & kTmaEpiRes) != 0;
+  uint8_t* stg = epi_smem + ew * tc_epi_stage_bytes(NT);
+  uint64_t* rbar = &res_bar[ew];
+  uint32_t rphase = 0;
+  constexpr int ACC = AccCfg<1>::ACC;
+  int it = group;
+  for (int tile = blockIdx.x + group * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, it += 2) {
+    const int acc = it & (ACC - 1);
+    const int n = tile / per_frame, rem = tile % per_frame;
+    const int y0 = (rem / tiles_x) * 16 + q * 4, x0 = (rem % tiles_x) * 8;     // this warp's 4 x 8 pixel box
+    if (lane == 0) {
+      bulk_wait_read0();                      // the previous tile's store has finished reading the staging tile
+      if (has_res) {
+        mbar_arrive_expect_tx(rbar, tc_epi_stage_bytes(NT));
+        tma_load_4d(stg, &maps.res, rbar, p.res_c_off + co0, x0, y0, n);
+      }
+    }
+    __syncwarp();
+    mbar_wait(&tmem_full[acc], (it / ACC) & 1);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT);
+    if (has_res) {
+      mbar_wait(rbar, rphase);
+      rphase ^= 1;
+    }
+#pragma unroll
+    for (int c0 = 0; c0 < NT; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(taddr + c0, r);
+      tmem_ld_wait();
+      if (c0 + 32 == NT) {                    // accumulator fully read: hand the TMEM stage back before the stores
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      }
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + s_bias[c0 + j];
+      if (has_res) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint4 t = *tc_epi_chunk<NT>(stg, lane, c0 / 8 + i);
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            v[i * 8 + 2 * k] += __low2float(h[k]);
+            v[i * 8 + 2 * k + 1] += __high2float(h[k]);
+          }
+        }
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 pk;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[i * 8 + 0], v[i * 8 + 1]);
+        __nv_bfloat162 h1 = __floats2bfloat162_rn(v[i * 8 + 2], v[i * 8 + 3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[i * 8 + 4], v[i * 8 + 5]);
+        __nv_bfloat162 h3 = __floats2bfloat162_rn(v[i * 8 + 6], v[i * 8 + 7]);
+        pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+        pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+        *tc_epi_chunk<NT>(stg, lane, c0 / 8 + i) = pk;
+      }
+    }
+    fence_proxy_async();                      // generic-proxy writes -> visible to the TMA store
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_4d(&maps.out, stg, p.out_c_off + co0, x0, y0, n);
+      bulk_commit_group();
+    }
+  }
+  if (lane == 0) bulk_wait0();                // all stores performed before the CTA's shared memory goes away
+  __syncwarp();
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 PFN_encodeTiled tc_get_encode();
+// decides whether the TMA epilogue applies (sets plan->tma_epi and the out/res tensor maps); 0 = direct epilogue
+int tc_epi_prepare(const ConvParams& p, int nt, bool ptrs_final, TcConvPlan* plan);
 // bf16 weight slab in shared-memory-image order [ntile][tap][chunk][NT rows x ROWB] with the TMA/UMMA XOR swizzle
 int tc_pack_weights(const float* w_oihw, int cin, int cout, int taps, int nt, void** d_out, std::vector<void*>* allocs);
 // stride-2 3x3 engine (conv_tc_s2.cu)
 bool tc_s2_supported(const ConvParams& p);
-int tc_s2_prepare(const ConvParams& p, const float* w_oihw, int sm_count, TcConvPlan* plan, std::vector<void*>* allocs);
+int tc_s2_prepare(const ConvParams& p, const float* w_oihw, int sm_count, bool ptrs_final, TcConvPlan* plan, std::vector<void*>* allocs);
 int tc_s2_launch(const TcConvPlan& plan, const ConvParams& p, cudaStream_t stream);
 
 }  // namespace b200romp
