@@ -88,6 +88,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_trigger();
   const int per_frame = tiles_x * tiles_y;
   const int nrings = stages >= 2 ? kMmaWarps : 1;   // MMA-issuing warps in use = private stage rings
 
@@ -98,6 +99,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       const uint8_t* wsrc = wpack + (size_t)blockIdx.y * Cfg::B_BYTES;
       for (int i = 0; i < Cfg::TAPS * Cfg::KCH; ++i)
         bulk_copy_g2s(sB + (size_t)i * Cfg::BTILE, wsrc + (size_t)i * Cfg::BTILE, Cfg::BTILE, b_full);
+      pdl_wait();                             // weights are constants; activations must wait for the predecessor grids
       // Each MMA warp owns a private stage ring (ring r = stages [ring_base(r), ring_base(r) + ring_size(r))): mbarrier
       // waits only see the phase parity, so a ring must have exactly one in-order consumer (TMA completions of
       // different stages arrive out of order, a shared ring would alias phases).  Tile i of this CTA goes to ring i & 1.
@@ -251,7 +253,7 @@ template <int KS, int CIN, int NT, bool PER_TAP, int KSPLIT>
 static int launch_inst(const TcConvPlan& plan, const ConvParams& p, cudaStream_t stream, bool set_attr_only) {
   auto kern = conv_tc_kernel<KS, CIN, NT, PER_TAP, KSPLIT>;
   if (set_attr_only) {
-    B2R_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
+    B2R_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 /* plans of one instantiation differ (TMA epilogue staging) */));
     return B200ROMP_OK;
   }
   CUtensorMap tm;
@@ -261,9 +263,8 @@ static int launch_inst(const TcConvPlan& plan, const ConvParams& p, cudaStream_t
   const int tiles_x = p.Wout / 8, tiles_y = p.Hout / 16;
   const int num_tiles = tiles_x * tiles_y * p.B;
   dim3 grid(std::min(plan.grid_x, num_tiles), plan.grid_y);
-  kern<<<grid, kTcThreads, plan.smem_bytes, stream>>>(tm, em, p, reinterpret_cast<const uint8_t*>(plan.d_wpack), tiles_x, tiles_y,
-                                               num_tiles, plan.stages, KSPLIT == 1 ? plan.tma_epi : 0);
-  B2R_CUDA_OK(cudaGetLastError());
+  B2R_CUDA_OK(tc_launch(kern, grid, plan.smem_bytes, stream, tm, em, p, reinterpret_cast<const uint8_t*>(plan.d_wpack), tiles_x,
+                        tiles_y, num_tiles, plan.stages, KSPLIT == 1 ? plan.tma_epi : 0));
   return B200ROMP_OK;
 }
 

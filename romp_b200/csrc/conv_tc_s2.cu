@@ -86,6 +86,7 @@ conv_tc_s2_kernel(const __grid_constant__ S2Maps maps, const __grid_constant__ T
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_trigger();
   const int per_frame = tiles_x * tiles_y;
   const int nrings = stages >= 2 ? kMmaWarps : 1;   // MMA-issuing warps in use = private stage rings
 
@@ -95,6 +96,7 @@ conv_tc_s2_kernel(const __grid_constant__ S2Maps maps, const __grid_constant__ T
       const uint8_t* wsrc = wpack + (size_t)blockIdx.y * Cfg::B_BYTES;
       for (int i = 0; i < 9 * Cfg::KCH; ++i)
         bulk_copy_g2s(sB + (size_t)i * Cfg::BTILE, wsrc + (size_t)i * Cfg::BTILE, Cfg::BTILE, b_full);
+      pdl_wait();                             // weights are constants; activations must wait for the predecessor grids
       int stage = 0, stage_other = 0;                  // one private stage ring per MMA warp (see conv_tc.cu)
       uint32_t phase = 0, phase_other = 0;   // (stage, phase) of the current tile's ring / of the other ring
       int it = 0;
@@ -190,7 +192,7 @@ template <int CIN, int NT, int KSPLIT>
 static int s2_inst(const TcConvPlan& plan, const ConvParams& p, cudaStream_t stream, bool attr) {
   auto kern = conv_tc_s2_kernel<CIN, NT, KSPLIT>;
   if (attr) {
-    B2R_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes));
+    B2R_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 /* plans of one instantiation differ (TMA epilogue staging) */));
     return B200ROMP_OK;
   }
   S2Maps maps;
@@ -200,9 +202,8 @@ static int s2_inst(const TcConvPlan& plan, const ConvParams& p, cudaStream_t str
   const int tiles_x = p.Wout / 8, tiles_y = p.Hout / 16;
   const int num_tiles = tiles_x * tiles_y * p.B;
   dim3 grid(std::min(plan.grid_x, num_tiles), plan.grid_y);
-  kern<<<grid, kTcThreads, plan.smem_bytes, stream>>>(maps, em, p, reinterpret_cast<const uint8_t*>(plan.d_wpack), tiles_x, tiles_y,
-                                                      num_tiles, plan.stages, KSPLIT == 1 ? plan.tma_epi : 0);
-  B2R_CUDA_OK(cudaGetLastError());
+  B2R_CUDA_OK(tc_launch(kern, grid, plan.smem_bytes, stream, maps, em, p, reinterpret_cast<const uint8_t*>(plan.d_wpack), tiles_x,
+                        tiles_y, num_tiles, plan.stages, KSPLIT == 1 ? plan.tma_epi : 0));
   return B200ROMP_OK;
 }
 

@@ -50,6 +50,11 @@ __device__ __forceinline__ bool elect_one() {
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
   return pred != 0;
 }
+// Programmatic dependent launch: the next conv of the stream may start its prologue (barrier init, TMEM allocation,
+// weight-slab copy - all independent of activations) while this grid drains; pdl_wait() then blocks until every
+// predecessor grid has completed and its writes are visible.  Both are no-ops for a launch without the attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -212,6 +217,7 @@ __device__ __forceinline__ void tc_epilogue_loop(const ConvParams& p, uint32_t t
   const int co0 = blockIdx.y * NT;
   const int up = p.up;
   const int Hf = p.Hout * up, Wf = p.Wout * up;
+  pdl_wait();                                 // residual reads / output writes must follow the predecessor grids
   int it = group;
   for (int tile = blockIdx.x + group * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, it += 2) {
     constexpr int ACC = AccCfg<KSPLIT>::ACC;
@@ -301,6 +307,7 @@ __device__ __forceinline__ void tc_epilogue_loop_tma(const ConvParams& p, const 
   uint64_t* rbar = &res_bar[ew];
   uint32_t rphase = 0;
   constexpr int ACC = AccCfg<1>::ACC;
+  pdl_wait();                                 // residual reads / output writes must follow the predecessor grids
   int it = group;
   for (int tile = blockIdx.x + group * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, it += 2) {
     const int acc = it & (ACC - 1);
@@ -371,6 +378,23 @@ __device__ __forceinline__ void tc_epilogue_loop_tma(const ConvParams& p, const 
   }
   if (lane == 0) bulk_wait0();                // all stores performed before the CTA's shared memory goes away
   __syncwarp();
+}
+
+// launch with the programmatic-stream-serialization attribute (see pdl_trigger / pdl_wait); B200ROMP_NO_PDL=1 disables it
+template <typename... KArgs, typename... Args>
+static inline cudaError_t tc_launch(void (*kern)(KArgs...), dim3 grid, int smem_bytes, cudaStream_t stream, Args&&... args) {
+  static const bool pdl = [] { const char* e = getenv("B200ROMP_NO_PDL"); return !(e && e[0] == '1'); }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
