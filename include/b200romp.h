@@ -86,6 +86,9 @@ int b200romp_net_read_tensor(b200romp_net* net, int tensor, int batch, void* dst
 int b200romp_net_describe(b200romp_net* net, char* buf, int len);
 /* Number of kernels one b200romp_net_run launches (gpu_launches accounting in bench.py). */
 int b200romp_net_num_launches(b200romp_net* net);
+/* Per-op device time of one net_run (measurement aid, bench.py / tools/op_profile.py): runs the ops one by one without
+ * the CUDA graph, `iters` passes, each op bracketed by CUDA events on `stream`; us_per_op[num_launches] receives the mean. */
+int b200romp_net_profile(b200romp_net* net, int batch, int iters, float* us_per_op, b200romp_stream stream);
 /* workspace bytes currently held */
 long long b200romp_net_workspace_bytes(b200romp_net* net);
 

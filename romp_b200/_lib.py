@@ -93,6 +93,7 @@ def load():
     _sig(lib.b200romp_net_describe, i32, vp, C.c_char_p, i32)
     _sig(lib.b200romp_net_num_launches, i32, vp)
     _sig(lib.b200romp_net_workspace_bytes, i64, vp)
+    _sig(lib.b200romp_net_profile, i32, vp, i32, i32, fp, vp)
     _sig(lib.b200romp_conv2d, i32, C.POINTER(ConvDesc), fp, fp, vp, i32, i32, i32, i32, vp, i32, i32, i32, vp, i32, i32, vp)
     _sig(lib.b200romp_parse, i32, vp, vp, i32, i32, i32, f32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp)
     _sig(lib.b200romp_parse_workspace_bytes, i64, i32)
@@ -127,7 +128,8 @@ EXPORTS = [
     "b200romp_version", "b200romp_last_error", "b200romp_device_info", "b200romp_net_create",
     "b200romp_net_destroy", "b200romp_net_add_tensor", "b200romp_net_add_const_tensor", "b200romp_net_add_conv",
     "b200romp_net_finalize", "b200romp_net_bind", "b200romp_net_run", "b200romp_net_read_tensor",
-    "b200romp_net_describe", "b200romp_net_num_launches", "b200romp_net_workspace_bytes", "b200romp_conv2d",
+    "b200romp_net_describe", "b200romp_net_num_launches", "b200romp_net_workspace_bytes", "b200romp_net_profile",
+    "b200romp_conv2d",
     "b200romp_parse", "b200romp_parse_workspace_bytes", "b200romp_smpl_create", "b200romp_smpl_destroy",
     "b200romp_smpl_workspace_floats", "b200romp_smpl_forward", "b200romp_project",
     "b200romp_bev_create", "b200romp_bev_destroy", "b200romp_bev_bv_input", "b200romp_bev_center3d",

@@ -377,6 +377,42 @@ int b200romp_net_run(b200romp_net* net, int batch, b200romp_stream stream_) {
   return B200ROMP_OK;
 }
 
+int b200romp_net_profile(b200romp_net* net, int batch, int iters, float* us_per_op, b200romp_stream stream_) {
+  B2R_REQUIRE(net && net->finalized && us_per_op && iters > 0, "profile: bad arguments");
+  B2R_REQUIRE(batch > 0 && batch <= net->max_batch, "profile: batch %d outside 1..%d", batch, net->max_batch);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B2R_CUDA_OK(cudaSetDevice(net->device));
+  const size_t n = net->ops.size();
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) B2R_CUDA_OK(cudaEventCreate(&e));
+  std::vector<double> acc(n, 0.0);
+  int rc = B200ROMP_OK;
+  for (int it = 0; it < iters + 1 && rc == B200ROMP_OK; ++it) {   // pass 0 warms up
+    cudaEventRecord(ev[0], stream);
+    for (size_t i = 0; i < n && rc == B200ROMP_OK; ++i) {
+      Op& op = net->ops[i];
+      ConvParams p;
+      rc = fill_params(net, op, batch, &p);
+      if (rc) break;
+      if (op.engine == B200ROMP_ENGINE_TCGEN05) rc = tc_conv_launch(op.tc, p, stream);
+      else rc = launch_conv_simt(p, op.d.ksize, op.d.stride, stream);
+      cudaEventRecord(ev[i + 1], stream);
+    }
+    if (rc) break;
+    if (cudaStreamSynchronize(stream) != cudaSuccess) { set_error("profile: %s", cudaGetErrorString(cudaGetLastError())); rc = B200ROMP_ECUDA; break; }
+    if (it == 0) continue;
+    for (size_t i = 0; i < n; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+      acc[i] += ms * 1000.0;
+    }
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  if (rc) return rc;
+  for (size_t i = 0; i < n; ++i) us_per_op[i] = (float)(acc[i] / iters);
+  return B200ROMP_OK;
+}
+
 int b200romp_net_read_tensor(b200romp_net* net, int tensor, int batch, void* dst, b200romp_stream stream) {
   B2R_REQUIRE(net && net->finalized && tensor >= 0 && tensor < (int)net->tensors.size(), "read_tensor: bad arguments");
   const Tensor& t = net->tensors[tensor];

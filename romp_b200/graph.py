@@ -107,6 +107,14 @@ class NetBuilder:
         self.lib.b200romp_net_describe(self.net, buf, len(buf))
         return buf.value.decode()
 
+    def profile(self, batch, iters=5, stream=None):
+        """Mean device time (us) of every op of one run, ops launched one by one (b200romp_net_profile)."""
+        n = self.lib.b200romp_net_num_launches(self.net)
+        us = (C.c_float * n)()
+        st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        _lib.check(self.lib.b200romp_net_profile(self.net, batch, iters, us, C.c_void_p(st)), "net_profile")
+        return list(us)
+
 
 def coord_maps(size=128):
     """get_coord_maps, model.py:8-37 -> [1,2,size,size]; ch0 varies along W, ch1 along H."""
