@@ -56,13 +56,13 @@ conv_tc_s2_kernel(const __grid_constant__ S2Maps maps, const __grid_constant__ T
   uint8_t* sB = smem;
   uint8_t* sA = smem + Cfg::B_BYTES;
   uint8_t* epi_smem = sA + (size_t)stages * Cfg::STAGE_BYTES;       // TMA-epilogue staging tiles, if any
-  uint64_t* full = reinterpret_cast<uint64_t*>(epi_smem + (tma_epi ? kEpiWarps * tc_epi_stage_bytes(NT) : 0));
+  uint64_t* full = reinterpret_cast<uint64_t*>(epi_smem + tc_epi_total_bytes(tma_epi, NT));
   uint64_t* empty = full + stages;
   uint64_t* b_full = empty + stages;
   uint64_t* tmem_full = b_full + 1;
   uint64_t* tmem_empty = tmem_full + kAccStages;
   uint64_t* res_bar = tmem_empty + kAccStages;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + kEpiWarps);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 2 * kEpiWarps);
   float* s_bias = reinterpret_cast<float*>(tmem_ptr + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -76,7 +76,7 @@ conv_tc_s2_kernel(const __grid_constant__ S2Maps maps, const __grid_constant__ T
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 4);
     }
-    for (int i = 0; i < kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
+    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (threadIdx.x >= kFirstEpiWarp * 32 && threadIdx.x < kFirstEpiWarp * 32 + NT)
@@ -241,7 +241,7 @@ int tc_s2_prepare(const ConvParams& p, const float* w_oihw, int sm_count, bool p
   // TMA epilogue only where it does not cost the second pipeline stage
   int epi_bytes = 0;
   if (tc_epi_prepare(p, nt, ptrs_final, plan)) {
-    epi_bytes = kEpiWarps * tc_epi_stage_bytes(nt);
+    epi_bytes = tc_epi_total_bytes(plan->tma_epi, nt);
     const int without = (budget - bbytes(nt)) / stage_bytes, with = (budget - bbytes(nt) - epi_bytes) / stage_bytes;
     if (with < 1 || (with < 2 && without >= 2)) { plan->tma_epi = 0; epi_bytes = 0; }
   }

@@ -281,8 +281,11 @@ __device__ __forceinline__ void tc_epilogue_loop(const ConvParams& p, uint32_t t
 struct TcEpiMaps {
   CUtensorMap out, res;
 };
-constexpr int kTmaEpiOut = 1, kTmaEpiRes = 2;
-__host__ __device__ constexpr int tc_epi_stage_bytes(int nt) { return 32 * nt * 2; }   // per epilogue warp
+constexpr int kTmaEpiOut = 1, kTmaEpiRes = 2, kTmaEpiDouble = 4;
+__host__ __device__ constexpr int tc_epi_stage_bytes(int nt) { return 32 * nt * 2; }   // per epilogue warp and buffer
+__host__ __device__ constexpr int tc_epi_total_bytes(int tma_epi, int nt) {
+  return tma_epi ? kEpiWarps * ((tma_epi & kTmaEpiDouble) ? 2 : 1) * tc_epi_stage_bytes(nt) : 0;
+}
 
 template <int NT>
 __device__ __forceinline__ uint4* tc_epi_chunk(uint8_t* stg, int row, int chunk) {
@@ -303,31 +306,41 @@ __device__ __forceinline__ void tc_epilogue_loop_tma(const ConvParams& p, const 
   const int q = warp & 3;
   const int co0 = blockIdx.y * NT;
   const bool has_res = (tma_epi & kTmaEpiRes) != 0;
-  uint8_t* stg = epi_smem + ew * tc_epi_stage_bytes(NT);
-  uint64_t* rbar = &res_bar[ew];
-  uint32_t rphase = 0;
+  // staging: one tile per warp, or two (kTmaEpiDouble) so that the residual of this warp's NEXT tile is already in
+  // flight while the current one is finished - hides the HBM latency of residuals that are not L2-resident
+  const int nbuf = (tma_epi & kTmaEpiDouble) ? 2 : 1;
+  uint8_t* stg0 = epi_smem + ew * nbuf * tc_epi_stage_bytes(NT);
+  uint64_t* rbar = &res_bar[ew * 2];
   constexpr int ACC = AccCfg<1>::ACC;
   pdl_wait();                                 // residual reads / output writes must follow the predecessor grids
-  int it = group;
-  for (int tile = blockIdx.x + group * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, it += 2) {
+  auto load_res = [&](int tile, int buf) {    // lane 0 only
+    const int n = tile / per_frame, rem = tile % per_frame;
+    mbar_arrive_expect_tx(&rbar[buf], tc_epi_stage_bytes(NT));
+    tma_load_4d(stg0 + buf * tc_epi_stage_bytes(NT), &maps.res, &rbar[buf], p.res_c_off + co0, (rem % tiles_x) * 8,
+                (rem / tiles_x) * 16 + q * 4, n);
+  };
+  const int first_tile = blockIdx.x + group * gridDim.x;
+  if (nbuf == 2 && has_res && lane == 0 && first_tile < num_tiles) load_res(first_tile, 0);
+  int it = group, t_local = 0;
+  for (int tile = first_tile; tile < num_tiles; tile += 2 * gridDim.x, it += 2, ++t_local) {
     const int acc = it & (ACC - 1);
     const int n = tile / per_frame, rem = tile % per_frame;
     const int y0 = (rem / tiles_x) * 16 + q * 4, x0 = (rem % tiles_x) * 8;     // this warp's 4 x 8 pixel box
+    const int buf = nbuf == 2 ? (t_local & 1) : 0;
+    uint8_t* stg = stg0 + buf * tc_epi_stage_bytes(NT);
+    const uint32_t rphase = (uint32_t)(nbuf == 2 ? (t_local >> 1) : t_local) & 1u;
     if (lane == 0) {
-      bulk_wait_read0();                      // the previous tile's store has finished reading the staging tile
+      bulk_wait_read0();                      // the previous tile's store has finished reading its staging tile
       if (has_res) {
-        mbar_arrive_expect_tx(rbar, tc_epi_stage_bytes(NT));
-        tma_load_4d(stg, &maps.res, rbar, p.res_c_off + co0, x0, y0, n);
+        if (nbuf == 1) load_res(tile, 0);
+        else if (tile + 2 * (int)gridDim.x < num_tiles) load_res(tile + 2 * gridDim.x, buf ^ 1);
       }
     }
     __syncwarp();
     mbar_wait(&tmem_full[acc], (it / ACC) & 1);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT);
-    if (has_res) {
-      mbar_wait(rbar, rphase);
-      rphase ^= 1;
-    }
+    if (has_res) mbar_wait(&rbar[buf], rphase);
 #pragma unroll
     for (int c0 = 0; c0 < NT; c0 += 32) {
       uint32_t r[32];
