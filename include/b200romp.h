@@ -75,6 +75,19 @@ int b200romp_net_add_tensor(b200romp_net* net, int H, int W, int C, int dtype, i
 int b200romp_net_add_const_tensor(b200romp_net* net, int H, int W, int C, int dtype, const void* host_data);
 /* weight: host fp32 [cout][cin][k][k] (PyTorch OIHW), bias: host fp32 [cout] or NULL. Returns op id. */
 int b200romp_net_add_conv(b200romp_net* net, const b200romp_conv_desc* desc, const float* weight, const float* bias);
+/* Fuse-layer summation of HighResolutionModule.forward (simple_romp/romp/model.py:226-244, nearest upsampling of the
+ * higher-index branches :188-197) as ONE elementwise op instead of a chain of residual adds:
+ *   out[n,y,x,c] = act( base[n,y,x,c] + sum_k term_k[n, y/up_k, x/up_k, c] ),  summed in fp32 in the order base, term 0, 1, ..
+ * All tensors NHWC with the same C (multiple of 8); term k is [H/up_k, W/up_k, C]; dtypes per tensor (bf16/fp32). */
+typedef struct b200romp_sum_desc {
+  int out, base;           /* output / identity-term tensor ids, both [H,W,C]                           */
+  int n_terms;             /* 1..4                                                                      */
+  int term[4];             /* tensor ids                                                                */
+  int up[4];               /* 1, 2, 4, 8: nearest-neighbour replication factor of term k                */
+  int relu;                /* 1 = ReLU after the sum (model.py:243)                                     */
+} b200romp_sum_desc;
+/* Returns op id (ops run in the order they were added, convs and sums alike). */
+int b200romp_net_add_sum(b200romp_net* net, const b200romp_sum_desc* desc);
 /* Packs weights for the chosen engines, uploads them, plans buffer reuse and allocates the workspace. */
 int b200romp_net_finalize(b200romp_net* net, int max_batch);
 int b200romp_net_bind(b200romp_net* net, int tensor, void* device_ptr);

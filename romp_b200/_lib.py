@@ -26,6 +26,11 @@ class ConvDesc(C.Structure):
         "ksize", "stride", "relu", "upsample", "input_norm", "pow_channel", "engine")]
 
 
+class SumDesc(C.Structure):
+    _fields_ = [("out", C.c_int), ("base", C.c_int), ("n_terms", C.c_int), ("term", C.c_int * 4), ("up", C.c_int * 4),
+                ("relu", C.c_int)]
+
+
 class BevWeights(C.Structure):
     _fields_ = [(n, C.POINTER(C.c_float)) for n in (
         "center_ref", "cam_ref", "coordmap", "anchors", "embed", "w0", "b0", "w1", "b1", "w2", "b2")]
@@ -86,6 +91,7 @@ def load():
     _sig(lib.b200romp_net_add_tensor, i32, vp, i32, i32, i32, i32, i32, i32)
     _sig(lib.b200romp_net_add_const_tensor, i32, vp, i32, i32, i32, i32, vp)
     _sig(lib.b200romp_net_add_conv, i32, vp, C.POINTER(ConvDesc), fp, fp)
+    _sig(lib.b200romp_net_add_sum, i32, vp, C.POINTER(SumDesc))
     _sig(lib.b200romp_net_finalize, i32, vp, i32)
     _sig(lib.b200romp_net_bind, i32, vp, i32, vp)
     _sig(lib.b200romp_net_run, i32, vp, i32, vp)
@@ -127,6 +133,7 @@ def check(rc, what=""):
 EXPORTS = [
     "b200romp_version", "b200romp_last_error", "b200romp_device_info", "b200romp_net_create",
     "b200romp_net_destroy", "b200romp_net_add_tensor", "b200romp_net_add_const_tensor", "b200romp_net_add_conv",
+    "b200romp_net_add_sum",
     "b200romp_net_finalize", "b200romp_net_bind", "b200romp_net_run", "b200romp_net_read_tensor",
     "b200romp_net_describe", "b200romp_net_num_launches", "b200romp_net_workspace_bytes", "b200romp_net_profile",
     "b200romp_conv2d",

@@ -125,6 +125,17 @@ __device__ __forceinline__ void conv_epilogue_store(const ConvParams& p, int n, 
   }
 }
 
+// fuse-layer sum op (conv_simt.cu)
+struct SumParams {
+  const void* base;
+  const void* term[4];
+  void* out;
+  int base_dt, term_dt[4], out_dt;
+  int n_terms, up[4];
+  int B, H, W, C, relu;
+};
+int launch_fuse_sum(const SumParams& p, cudaStream_t stream);
+
 // engines implemented in other translation units
 int launch_conv_simt(const ConvParams& p, int ksize, int stride, cudaStream_t stream);
 

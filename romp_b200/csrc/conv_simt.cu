@@ -12,6 +12,8 @@
 // Tiling: one CTA = 8x8 output pixels x 64 output channels, 256 threads, each thread a 4(pixel) x
 // 4(channel) register tile; input halo tile and weight slab staged in shared memory in chunks of 8
 // input channels.  HBM/L2 traffic per CTA: input halo once per 64-channel slab, weights once per tile.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace b200romp {
@@ -214,6 +216,64 @@ int launch_conv_simt(const ConvParams& p, int ksize, int stride, cudaStream_t st
     set_error("conv_simt: unsupported ksize=%d stride=%d", ksize, stride);
     return B200ROMP_EINVAL;
   }
+  B2R_CUDA_OK(cudaGetLastError());
+  return B200ROMP_OK;
+}
+
+// ---- fuse-layer sum (b200romp_net_add_sum): HBM-bound elementwise op, thread = 8 channels of one output pixel -------
+__device__ __forceinline__ void load8(const void* p, int dt, size_t idx, float (&v)[8]) {
+  if (dt == B200ROMP_F32) {
+    const float4 a = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + idx)[0];
+    const float4 b = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + idx)[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+    const uint4 t = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p) + idx);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[2 * k] = __low2float(h[k]); v[2 * k + 1] = __high2float(h[k]); }
+  }
+}
+
+__global__ void __launch_bounds__(256) fuse_sum_kernel(const SumParams p) {
+  const int c8n = p.C / 8;
+  const size_t total = (size_t)p.B * p.H * p.W * c8n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % c8n);
+    const size_t pix = i / c8n;
+    const int x = (int)(pix % p.W), y = (int)((pix / p.W) % p.H), n = (int)(pix / ((size_t)p.W * p.H));
+    float s[8], t[8];
+    load8(p.base, p.base_dt, pix * p.C + c8 * 8, s);
+    for (int k = 0; k < p.n_terms; ++k) {
+      const int u = p.up[k];
+      const size_t tp = ((size_t)n * (p.H / u) + y / u) * (p.W / u) + x / u;
+      load8(p.term[k], p.term_dt[k], tp * p.C + c8 * 8, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += t[j];
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] = fmaxf(s[j], 0.f);
+    }
+    const size_t oi = pix * p.C + c8 * 8;
+    if (p.out_dt == B200ROMP_F32) {
+      float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + oi);
+      o[0] = make_float4(s[0], s[1], s[2], s[3]);
+      o[1] = make_float4(s[4], s[5], s[6], s[7]);
+    } else {
+      uint4 pk;
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(s[0], s[1]), h1 = __floats2bfloat162_rn(s[2], s[3]);
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(s[4], s[5]), h3 = __floats2bfloat162_rn(s[6], s[7]);
+      pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+      pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + oi) = pk;
+    }
+  }
+}
+
+int launch_fuse_sum(const SumParams& p, cudaStream_t stream) {
+  const size_t total = (size_t)p.B * p.H * p.W * (p.C / 8);
+  const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)148 * 16);
+  fuse_sum_kernel<<<blocks, 256, 0, stream>>>(p);
   B2R_CUDA_OK(cudaGetLastError());
   return B200ROMP_OK;
 }

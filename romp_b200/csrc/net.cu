@@ -38,6 +38,8 @@ struct Tensor {
 };
 
 struct Op {
+  int kind = 0;                        // 0 = conv (d), 1 = fuse-layer sum (sum; d.out / d.in mirror out / base, d.res = -1)
+  b200romp_sum_desc sum;
   b200romp_conv_desc d;
   std::vector<float> w_host, b_host;   // OIHW fp32, [cout]
   float* d_w_simt = nullptr;           // [tap][cin][coutPad]
@@ -203,6 +205,65 @@ int b200romp_net_add_conv(b200romp_net* net, const b200romp_conv_desc* desc, con
   return (int)net->ops.size() - 1;
 }
 
+int b200romp_net_add_sum(b200romp_net* net, const b200romp_sum_desc* desc) {
+  B2R_REQUIRE(net && desc && !net->finalized, "add_sum: bad arguments or net already finalized");
+  const auto& T = net->tensors;
+  const int nT = (int)T.size();
+  B2R_REQUIRE(desc->out >= 0 && desc->out < nT && desc->base >= 0 && desc->base < nT, "add_sum: tensor id out of range");
+  B2R_REQUIRE(desc->n_terms >= 1 && desc->n_terms <= 4, "add_sum: n_terms must be 1..4");
+  const Tensor& to = T[desc->out];
+  const Tensor& tb = T[desc->base];
+  B2R_REQUIRE(!to.nchw && !tb.nchw && to.dtype != B200ROMP_U8 && tb.dtype != B200ROMP_U8, "add_sum: NHWC bf16/fp32 tensors only");
+  B2R_REQUIRE(to.C % 8 == 0 && tb.H == to.H && tb.W == to.W && tb.C == to.C, "add_sum: base/out shape mismatch (C %% 8 == 0)");
+  for (int k = 0; k < desc->n_terms; ++k) {
+    B2R_REQUIRE(desc->term[k] >= 0 && desc->term[k] < nT, "add_sum: term tensor id out of range");
+    const Tensor& tt = T[desc->term[k]];
+    const int u = desc->up[k];
+    B2R_REQUIRE(u == 1 || u == 2 || u == 4 || u == 8, "add_sum: up must be 1,2,4,8");
+    B2R_REQUIRE(!tt.nchw && tt.dtype != B200ROMP_U8 && tt.C == to.C && tt.H * u == to.H && tt.W * u == to.W,
+                "add_sum: term %d is %dx%dx%d, expected %dx%dx%d", k, tt.H, tt.W, tt.C, to.H / u, to.W / u, to.C);
+  }
+  Op op;
+  op.kind = 1;
+  op.sum = *desc;
+  memset(&op.d, 0, sizeof(op.d));
+  op.d.out = desc->out; op.d.in = desc->base; op.d.res = -1;
+  net->ops.push_back(std::move(op));
+  return (int)net->ops.size() - 1;
+}
+
+static int fill_sum_params(b200romp_net* net, const Op& op, int batch, SumParams* out) {
+  SumParams p;
+  memset(&p, 0, sizeof(p));
+  const Tensor& to = net->tensors[op.sum.out];
+  const Tensor& tb = net->tensors[op.sum.base];
+  B2R_REQUIRE(to.ptr && tb.ptr, "sum op: unbound tensor");
+  p.base = tb.ptr; p.base_dt = tb.dtype; p.out = to.ptr; p.out_dt = to.dtype;
+  p.n_terms = op.sum.n_terms;
+  for (int k = 0; k < p.n_terms; ++k) {
+    const Tensor& tt = net->tensors[op.sum.term[k]];
+    B2R_REQUIRE(tt.ptr, "sum op: unbound term tensor");
+    p.term[k] = tt.ptr; p.term_dt[k] = tt.dtype; p.up[k] = op.sum.up[k];
+  }
+  p.B = batch; p.H = to.H; p.W = to.W; p.C = to.C; p.relu = op.sum.relu;
+  *out = p;
+  return B200ROMP_OK;
+}
+
+// one op of the plan on `stream`
+static int enqueue_op(b200romp_net* net, Op& op, int batch, cudaStream_t stream) {
+  if (op.kind == 1) {
+    SumParams sp;
+    int rc = fill_sum_params(net, op, batch, &sp);
+    return rc ? rc : launch_fuse_sum(sp, stream);
+  }
+  ConvParams p;
+  int rc = fill_params(net, op, batch, &p);
+  if (rc) return rc;
+  if (op.engine == B200ROMP_ENGINE_TCGEN05) return tc_conv_launch(op.tc, p, stream);
+  return launch_conv_simt(p, op.d.ksize, op.d.stride, stream);
+}
+
 static int upload_simt_weights(b200romp_net* net, Op& op) {
   const b200romp_conv_desc& d = op.d;
   const int taps = d.ksize == 13 ? 3 : d.ksize * d.ksize;
@@ -235,6 +296,12 @@ int b200romp_net_finalize(b200romp_net* net, int max_batch) {
     to.last_use = std::max(to.last_use, i);
     net->tensors[d.in].last_use = std::max(net->tensors[d.in].last_use, i);
     if (d.res >= 0) net->tensors[d.res].last_use = std::max(net->tensors[d.res].last_use, i);
+    if (net->ops[i].kind == 1)
+      for (int k = 0; k < net->ops[i].sum.n_terms; ++k) {
+        Tensor& tt = net->tensors[net->ops[i].sum.term[k]];
+        B2R_REQUIRE(tt.external || tt.constant || (tt.first_def >= 0 && tt.first_def < i), "op %d sums tensor %d before it is written", i, net->ops[i].sum.term[k]);
+        tt.last_use = std::max(tt.last_use, i);
+      }
   }
   for (int i = 0; i < nO; ++i) {
     const b200romp_conv_desc& d = net->ops[i].d;
@@ -284,6 +351,7 @@ int b200romp_net_finalize(b200romp_net* net, int max_batch) {
   // ---- engine resolution + weight upload
   for (int i = 0; i < nO; ++i) {
     Op& op = net->ops[i];
+    if (op.kind == 1) continue;
     int rc = upload_simt_weights(net, op);
     if (rc) return rc;
     op.engine = B200ROMP_ENGINE_SIMT;
@@ -328,12 +396,7 @@ int b200romp_net_bind(b200romp_net* net, int tensor, void* device_ptr) {
 
 static int enqueue_all(b200romp_net* net, int batch, cudaStream_t stream) {
   for (size_t i = 0; i < net->ops.size(); ++i) {
-    Op& op = net->ops[i];
-    ConvParams p;
-    int rc = fill_params(net, op, batch, &p);
-    if (rc) return rc;
-    if (op.engine == B200ROMP_ENGINE_TCGEN05) rc = tc_conv_launch(op.tc, p, stream);
-    else rc = launch_conv_simt(p, op.d.ksize, op.d.stride, stream);
+    int rc = enqueue_op(net, net->ops[i], batch, stream);
     if (rc) return rc;
   }
   return B200ROMP_OK;
@@ -390,12 +453,7 @@ int b200romp_net_profile(b200romp_net* net, int batch, int iters, float* us_per_
   for (int it = 0; it < iters + 1 && rc == B200ROMP_OK; ++it) {   // pass 0 warms up
     cudaEventRecord(ev[0], stream);
     for (size_t i = 0; i < n && rc == B200ROMP_OK; ++i) {
-      Op& op = net->ops[i];
-      ConvParams p;
-      rc = fill_params(net, op, batch, &p);
-      if (rc) break;
-      if (op.engine == B200ROMP_ENGINE_TCGEN05) rc = tc_conv_launch(op.tc, p, stream);
-      else rc = launch_conv_simt(p, op.d.ksize, op.d.stride, stream);
+      rc = enqueue_op(net, net->ops[i], batch, stream);
       cudaEventRecord(ev[i + 1], stream);
     }
     if (rc) break;
@@ -431,6 +489,13 @@ int b200romp_net_describe(b200romp_net* net, char* buf, int len) {
     const b200romp_conv_desc& d = op.d;
     const Tensor& ti = net->tensors[d.in];
     const Tensor& to = net->tensors[d.out];
+    if (op.kind == 1) {
+      int n = snprintf(line, sizeof(line), "op%03zu sum     out t%d[%dx%dx%d] = relu%d( t%d", i, op.sum.out, to.H, to.W, to.C, op.sum.relu, op.sum.base);
+      for (int k = 0; k < op.sum.n_terms; ++k) n += snprintf(line + n, sizeof(line) - n, " + up%d(t%d)", op.sum.up[k], op.sum.term[k]);
+      snprintf(line + n, sizeof(line) - n, " )\n");
+      s += line;
+      continue;
+    }
     snprintf(line, sizeof(line), "op%03zu %s k%d s%d %4d->%-4d in t%d[%dx%dx%d]+%d out t%d[%dx%dx%d]+%d res t%d up%d relu%d%s\n", i,
              op.engine == B200ROMP_ENGINE_TCGEN05 ? "tcgen05" : "simt   ", d.ksize, d.stride, d.cin, d.cout, d.in, ti.H,
              ti.W, ti.C, d.in_c_off, d.out, to.H, to.W, to.C, d.out_c_off, d.res, d.upsample, d.relu,

@@ -16,7 +16,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib
-from ._lib import BF16, F32, U8, ConvDesc
+from ._lib import BF16, F32, U8, ConvDesc, SumDesc
 
 BN_EPS = 1e-5
 
@@ -99,6 +99,15 @@ class NetBuilder:
         self.flops_per_frame += 2 * cout * cin * kh * kw * (Ho // up) * (Wo // up)
         return out
 
+    def sum(self, base, terms, ups, relu=True, out_dtype=None, name=None):
+        """out = act(base + sum_k nearest_up(terms[k], ups[k])) - the HRNet fuse-layer summation (model.py:226-244)."""
+        H, W, Cc, _ = self.shape[base]
+        out = self.tensor(H, W, Cc, out_dtype, name=name)
+        d = SumDesc(out, base, len(terms), (C.c_int * 4)(*(list(terms) + [0] * (4 - len(terms)))),
+                    (C.c_int * 4)(*(list(ups) + [1] * (4 - len(ups)))), int(relu))
+        _lib.check(self.lib.b200romp_net_add_sum(self.net, C.byref(d)), "add_sum")
+        return out
+
     def finalize(self, max_batch):
         _lib.check(self.lib.b200romp_net_finalize(self.net, max_batch), "net_finalize")
 
@@ -146,27 +155,31 @@ def build_backbone(nb: NetBuilder, sd, in_dtype):
         return cb(t, q + "conv2", q + "bn2", relu=True, res=x)
 
     def hr_module(xs, q, nbr, multi=True):
-        """HighResolutionModule.forward model.py:226-244; fuse sum kept in fp32 until the final ReLU."""
+        """HighResolutionModule.forward model.py:226-244.  Every fuse term is produced at its own resolution (1x1 conv
+        of a lower-resolution branch / chain of stride-2 3x3 convs of a higher-resolution one) and ONE sum op per
+        output branch adds them in fp32 to the identity term, upsampling on the fly, then ReLU (model.py:243)."""
         xs = list(xs)
         for b in range(nbr):
             for k in range(4):
                 xs[b] = basic_block(xs[b], f"{q}branches.{b}.{k}.")
         outs = []
         for i in range(nbr if multi else 1):
-            acc = xs[i]                       # identity term (model.py:236-239) seeds the running sum
-            terms = [j for j in range(nbr) if j != i]
-            for t_idx, j in enumerate(terms):
-                last = t_idx == len(terms) - 1
-                od = act if last else F32
+            terms, ups = [], []
+            for j in range(nbr):
+                if j == i:
+                    continue                  # identity term (model.py:236-239) is the base of the sum
                 r = f"{q}fuse_layers.{i}.{j}."
-                if j > i:                     # 1x1 conv + BN + nearest upsample (model.py:188-197)
-                    acc = cb(xs[j], r + "0", r + "1", res=acc, up=2 ** (j - i), relu=last, out_dtype=od)
+                if j > i:                     # 1x1 conv + BN, nearest upsample folded into the sum (model.py:188-197)
+                    terms.append(cb(xs[j], r + "0", r + "1"))
+                    ups.append(2 ** (j - i))
                 else:                         # chain of stride-2 3x3 convs (model.py:200-218)
                     t = xs[j]
                     for k in range(i - j - 1):
                         t = cb(t, f"{r}{k}.0", f"{r}{k}.1", stride=2, relu=True)
                     k = i - j - 1
-                    acc = cb(t, f"{r}{k}.0", f"{r}{k}.1", stride=2, res=acc, relu=last, out_dtype=od)
+                    terms.append(cb(t, f"{r}{k}.0", f"{r}{k}.1", stride=2))
+                    ups.append(1)
+            acc = nb.sum(xs[i], terms, ups, relu=True)
             outs.append(acc)
         return outs
 

@@ -38,6 +38,9 @@ def main():
     lines = [l for l in nb.describe().splitlines() if l.startswith("op")]
     rows = []
     for l, t in zip(lines, us):
+        if " sum " in l:
+            rows.append((t, 0.0, l))
+            continue
         m = re.search(r"k(\d+) s(\d) +(\d+)->(\d+) +in t\d+\[(\d+)x(\d+)x\d+\]", l)
         k, s, cin, cout, H, W = (int(x) for x in m.groups())
         k2 = 3 if k == 13 else k * k
@@ -50,6 +53,11 @@ def main():
     # by class
     cls = {}
     for t, f, l in rows:
+        if " sum " in l:
+            ms = re.search(r"out t\d+\[(\d+)x\d+x(\d+)\]", l)
+            a = cls.setdefault(f"sum @{ms.group(1)} c{ms.group(2)} terms{l.count('up')}", [0, 0.0, 0.0])
+            a[0] += 1; a[1] += t
+            continue
         m = re.search(r"(tcgen05|simt) +k(\d+) s(\d) +(\d+)->(\d+) +in t\d+\[(\d+)x", l)
         key = f"{m.group(1)} k{m.group(2)} s{m.group(3)} {m.group(4)}->{m.group(5)} @{m.group(6)}" + (" epi" + l.split("epi")[1][0] if "epi" in l else "") + \
               (" up" + re.search(r"up(\d)", l).group(1))
