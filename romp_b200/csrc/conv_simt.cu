@@ -234,21 +234,25 @@ __device__ __forceinline__ void load8(const void* p, int dt, size_t idx, float (
   }
 }
 
-__global__ void __launch_bounds__(256) fuse_sum_kernel(const SumParams p) {
-  const int c8n = p.C / 8;
-  const size_t total = (size_t)p.B * p.H * p.W * c8n;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % c8n);
-    const size_t pix = i / c8n;
-    const int x = (int)(pix % p.W), y = (int)((pix / p.W) % p.H), n = (int)(pix / ((size_t)p.W * p.H));
+// grid: x = 16 B chunks of one output row (W * C/8), y = rows (B * H): only 32-bit index arithmetic, up factors as shifts
+__global__ void __launch_bounds__(256) fuse_sum_kernel(const SumParams p, int c8n, int4 up_shift) {
+  const int ush[4] = {up_shift.x, up_shift.y, up_shift.z, up_shift.w};
+  for (int row = blockIdx.y; row < p.B * p.H; row += gridDim.y) {   // row = n * H + y
+  const int n = row / p.H, y = row - n * p.H;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.W * c8n; i += gridDim.x * blockDim.x) {
+    const int x = i / c8n, c8 = i - x * c8n;
+    const size_t pix = (size_t)row * p.W + x;
     float s[8], t[8];
     load8(p.base, p.base_dt, pix * p.C + c8 * 8, s);
-    for (int k = 0; k < p.n_terms; ++k) {
-      const int u = p.up[k];
-      const size_t tp = ((size_t)n * (p.H / u) + y / u) * (p.W / u) + x / u;
-      load8(p.term[k], p.term_dt[k], tp * p.C + c8 * 8, t);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s[j] += t[j];
+    for (int k = 0; k < 4; ++k) {
+      if (k < p.n_terms) {
+        const int sh = ush[k];
+        const size_t tp = ((size_t)n * (p.H >> sh) + (y >> sh)) * (p.W >> sh) + (x >> sh);
+        load8(p.term[k], p.term_dt[k], tp * p.C + c8 * 8, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] += t[j];
+      }
     }
     if (p.relu) {
 #pragma unroll
@@ -268,12 +272,17 @@ __global__ void __launch_bounds__(256) fuse_sum_kernel(const SumParams p) {
       *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + oi) = pk;
     }
   }
+  }
 }
 
 int launch_fuse_sum(const SumParams& p, cudaStream_t stream) {
-  const size_t total = (size_t)p.B * p.H * p.W * (p.C / 8);
-  const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)148 * 16);
-  fuse_sum_kernel<<<blocks, 256, 0, stream>>>(p);
+  const int c8n = p.C / 8;
+  auto lg = [](int u) { return u == 8 ? 3 : u == 4 ? 2 : u == 2 ? 1 : 0; };
+  const int4 sh = make_int4(lg(p.up[0]), lg(p.up[1]), lg(p.up[2]), lg(p.up[3]));
+  const int per_row = p.W * c8n;
+  const int threads = per_row >= 256 ? 256 : (per_row + 31) / 32 * 32;
+  dim3 grid((per_row + threads - 1) / threads, std::min(p.B * p.H, 65535));
+  fuse_sum_kernel<<<grid, threads, 0, stream>>>(p, c8n, sh);
   B2R_CUDA_OK(cudaGetLastError());
   return B200ROMP_OK;
 }

@@ -67,7 +67,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 2 * kEpiWarps);
   float* s_bias = reinterpret_cast<float*>(tmem_ptr + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     for (int i = 0; i < stages; ++i) {
       mbar_init(&full[i], 1);
@@ -383,6 +383,7 @@ int tc_conv_prepare(const ConvParams& p, int ksize, int stride, const float* w_o
 }
 
 int tc_conv_launch(const TcConvPlan& plan, const ConvParams& p, cudaStream_t stream) {
+  if (plan.kind == 33) return tc_stem_launch(plan, p, stream);
   if (plan.kind % 10 == 2) return tc_s2_launch(plan, p, stream);
   return dispatch<false>(plan, p, stream, false);
 }

@@ -65,7 +65,7 @@ conv_tc_s2_kernel(const __grid_constant__ S2Maps maps, const __grid_constant__ T
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 2 * kEpiWarps);
   float* s_bias = reinterpret_cast<float*>(tmem_ptr + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     for (int i = 0; i < stages; ++i) {
       mbar_init(&full[i], 1);

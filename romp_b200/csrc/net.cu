@@ -357,22 +357,33 @@ int b200romp_net_finalize(b200romp_net* net, int max_batch) {
     op.engine = B200ROMP_ENGINE_SIMT;
     const Tensor& ti = net->tensors[op.d.in];
     const Tensor& to = net->tensors[op.d.out];
+    const bool stem_like = ti.dtype == B200ROMP_U8 && op.d.cin == 3 && op.d.ksize == 3 && op.d.stride == 2;
     const bool want_tc = op.d.engine == B200ROMP_ENGINE_TCGEN05 ||
-                         (op.d.engine == B200ROMP_ENGINE_AUTO && ti.dtype == B200ROMP_BF16);
+                         (op.d.engine == B200ROMP_ENGINE_AUTO && (ti.dtype == B200ROMP_BF16 || stem_like));
     if (want_tc) {
       ConvParams p;
       // The TMA tensor map of the INPUT is baked now, so the input must be an internal tensor (final pointer);
       // outputs / residuals are plain pointers read from ConvParams at launch and may be external (map outputs).
-      bool ext_out_unbound = false;
+      // (The stem engine gathers its u8 input with plain loads: its input may be external, its output must be internal.)
+      bool ext_out_unbound = false, ext_in_unbound = false;
       if (to.external && to.ptr == nullptr) {   // give fill_params a placeholder; the real pointer comes at run time
         net->tensors[op.d.out].ptr = reinterpret_cast<void*>(16);
         ext_out_unbound = true;
       }
-      const bool params_ok = !ti.external && fill_params(net, op, max_batch, &p) == B200ROMP_OK;
+      if (stem_like && ti.external && ti.ptr == nullptr) {
+        net->tensors[op.d.in].ptr = reinterpret_cast<void*>(16);
+        ext_in_unbound = true;
+      }
+      const bool params_ok = (!ti.external || stem_like) && fill_params(net, op, max_batch, &p) == B200ROMP_OK;
       if (ext_out_unbound) net->tensors[op.d.out].ptr = nullptr;
-      if (params_ok &&
+      if (ext_in_unbound) net->tensors[op.d.in].ptr = nullptr;
+      const bool ptrs_final = !to.external && (op.d.res < 0 || !net->tensors[op.d.res].external);
+      if (params_ok && stem_like && ptrs_final && tc_stem_supported(p, op.d.ksize, op.d.stride)) {
+        rc = tc_stem_prepare(p, op.w_host.data(), net->sm_count, ptrs_final, &op.tc, &net->device_allocs);
+        if (rc == B200ROMP_OK) op.engine = B200ROMP_ENGINE_TCGEN05;
+        else if (op.d.engine == B200ROMP_ENGINE_TCGEN05) return rc;
+      } else if (params_ok && !stem_like &&
           tc_conv_supported(p, op.d.ksize, op.d.stride)) {
-        const bool ptrs_final = !to.external && (op.d.res < 0 || !net->tensors[op.d.res].external);
         rc = tc_conv_prepare(p, op.d.ksize, op.d.stride, op.w_host.data(), net->sm_count, ptrs_final, &op.tc, &net->device_allocs);
         if (rc == B200ROMP_OK) op.engine = B200ROMP_ENGINE_TCGEN05;
         else if (op.d.engine == B200ROMP_ENGINE_TCGEN05) return rc;

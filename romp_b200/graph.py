@@ -141,7 +141,7 @@ def build_backbone(nb: NetBuilder, sd, in_dtype):
 
     frames = nb.tensor(512, 512, 3, in_dtype, external=1, name="frames")
     p = "backbone."
-    x = cb(frames, p + "conv1", p + "bn1", stride=2, relu=True, input_norm=1, engine=_lib.ENGINE_SIMT)   # model.py:385-387
+    x = cb(frames, p + "conv1", p + "bn1", stride=2, relu=True, input_norm=1)   # model.py:385-387
     x = cb(x, p + "conv2", p + "bn2", stride=2, relu=True)                                                # :388-390
     for i in range(4):                                                                                     # layer1, :391
         q = f"{p}layer1.{i}."
