@@ -15,6 +15,8 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "conv_tc.cuh"
+#include "tc_device.cuh"   // mbarrier / bulk-copy helpers for the fuse-sum ring
 
 namespace b200romp {
 
@@ -234,44 +236,114 @@ __device__ __forceinline__ void load8(const void* p, int dt, size_t idx, float (
   }
 }
 
-// grid: x = 16 B chunks of one output row (W * C/8), y = rows (B * H): only 32-bit index arithmetic, up factors as shifts
+__device__ __forceinline__ void sum_finish_store(const SumParams& p, float (&s)[8], size_t oi) {
+  if (p.relu) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = fmaxf(s[j], 0.f);
+  }
+  if (p.out_dt == B200ROMP_F32) {
+    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + oi);
+    o[0] = make_float4(s[0], s[1], s[2], s[3]);
+    o[1] = make_float4(s[4], s[5], s[6], s[7]);
+  } else {
+    uint4 pk;
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(s[0], s[1]), h1 = __floats2bfloat162_rn(s[2], s[3]);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(s[4], s[5]), h3 = __floats2bfloat162_rn(s[6], s[7]);
+    pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+    pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + oi) = pk;
+  }
+}
+
+// Fallback: grid x = 16 B chunks of one output row (W * C/8), y = rows (B * H); one chunk per thread.
 __global__ void __launch_bounds__(256) fuse_sum_kernel(const SumParams p, int c8n, int4 up_shift) {
   const int ush[4] = {up_shift.x, up_shift.y, up_shift.z, up_shift.w};
   for (int row = blockIdx.y; row < p.B * p.H; row += gridDim.y) {   // row = n * H + y
-  const int n = row / p.H, y = row - n * p.H;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.W * c8n; i += gridDim.x * blockDim.x) {
-    const int x = i / c8n, c8 = i - x * c8n;
-    const size_t pix = (size_t)row * p.W + x;
-    float s[8], t[8];
-    load8(p.base, p.base_dt, pix * p.C + c8 * 8, s);
+    const int n = row / p.H, y = row - n * p.H;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.W * c8n; i += gridDim.x * blockDim.x) {
+      const int x = i / c8n, c8 = i - x * c8n;
+      const size_t pix = (size_t)row * p.W + x;
+      float s[8], t[8];
+      load8(p.base, p.base_dt, pix * p.C + c8 * 8, s);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (k < p.n_terms) {
-        const int sh = ush[k];
-        const size_t tp = ((size_t)n * (p.H >> sh) + (y >> sh)) * (p.W >> sh) + (x >> sh);
-        load8(p.term[k], p.term_dt[k], tp * p.C + c8 * 8, t);
+      for (int k = 0; k < 4; ++k) {
+        if (k < p.n_terms) {
+          const int sh = ush[k];
+          const size_t tp = ((size_t)n * (p.H >> sh) + (y >> sh)) * (p.W >> sh) + (x >> sh);
+          load8(p.term[k], p.term_dt[k], tp * p.C + c8 * 8, t);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s[j] += t[j];
+          for (int j = 0; j < 8; ++j) s[j] += t[j];
+        }
       }
-    }
-    if (p.relu) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) s[j] = fmaxf(s[j], 0.f);
-    }
-    const size_t oi = pix * p.C + c8 * 8;
-    if (p.out_dt == B200ROMP_F32) {
-      float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + oi);
-      o[0] = make_float4(s[0], s[1], s[2], s[3]);
-      o[1] = make_float4(s[4], s[5], s[6], s[7]);
-    } else {
-      uint4 pk;
-      __nv_bfloat162 h0 = __floats2bfloat162_rn(s[0], s[1]), h1 = __floats2bfloat162_rn(s[2], s[3]);
-      __nv_bfloat162 h2 = __floats2bfloat162_rn(s[4], s[5]), h3 = __floats2bfloat162_rn(s[6], s[7]);
-      pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-      pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + oi) = pk;
+      sum_finish_store(p, s, pix * p.C + c8 * 8);
     }
   }
+}
+
+// Main version: persistent blocks stream the base tensor row by row through a kSumStages-deep shared-memory ring filled by
+// 1-D bulk async copies (cp.async.bulk + mbarrier).  One 16 B load per thread keeps only ~32 KB per SM in flight - measured
+// 2.3 TB/s; the ring keeps blocks/SM x stages x row bytes (~100 KB) in flight without spending registers.  The
+// low-resolution terms are read with plain loads (re-used across up^2 outputs, L1/L2 hits).
+constexpr int kSumStages = 4;
+__global__ void __launch_bounds__(256) fuse_sum_pipe_kernel(const SumParams p, int c8n, int4 up_shift, int row_bytes) {
+  extern __shared__ uint8_t sum_smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sum_smem_raw) + 127) & ~(uintptr_t)127);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + (size_t)kSumStages * row_bytes);
+  uint64_t* empty = full + kSumStages;
+  const int ush[4] = {up_shift.x, up_shift.y, up_shift.z, up_shift.w};
+  const int rows = p.B * p.H, per_row = p.W * c8n;
+  const int lane = threadIdx.x & 31;
+  const uint8_t* base = reinterpret_cast<const uint8_t*>(p.base);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kSumStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], blockDim.x / 32);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int d = 0; d < kSumStages; ++d) {
+      const int r = blockIdx.x + d * gridDim.x;
+      if (r < rows) {
+        mbar_arrive_expect_tx(&full[d], row_bytes);
+        bulk_copy_g2s(sm + (size_t)d * row_bytes, base + (size_t)r * row_bytes, row_bytes, &full[d]);
+      }
+    }
+  }
+  int iter = 0;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x, ++iter) {
+    const int st = iter % kSumStages;
+    const uint32_t ph = (uint32_t)(iter / kSumStages) & 1u;
+    const int n = row / p.H, y = row - n * p.H;
+    const uint8_t* srow = sm + (size_t)st * row_bytes;
+    mbar_wait(&full[st], ph);
+    for (int i = threadIdx.x; i < per_row; i += blockDim.x) {
+      const int x = i / c8n, c8 = i - x * c8n;
+      float s[8], t[8];
+      load8(srow, p.base_dt, (size_t)i * 8, s);             // generic load from shared memory
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < p.n_terms) {
+          const int sh = ush[k];
+          const size_t tp = ((size_t)n * (p.H >> sh) + (y >> sh)) * (p.W >> sh) + (x >> sh);
+          load8(p.term[k], p.term_dt[k], tp * p.C + c8 * 8, t);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s[j] += t[j];
+        }
+      }
+      sum_finish_store(p, s, ((size_t)row * p.W + x) * p.C + c8 * 8);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);
+    if (threadIdx.x == 0) {
+      const int next = row + kSumStages * gridDim.x;
+      if (next < rows) {
+        mbar_wait(&empty[st], ph);                          // every warp is done with this stage
+        mbar_arrive_expect_tx(&full[st], row_bytes);
+        bulk_copy_g2s(sm + (size_t)st * row_bytes, base + (size_t)next * row_bytes, row_bytes, &full[st]);
+      }
+    }
   }
 }
 
@@ -280,6 +352,21 @@ int launch_fuse_sum(const SumParams& p, cudaStream_t stream) {
   auto lg = [](int u) { return u == 8 ? 3 : u == 4 ? 2 : u == 2 ? 1 : 0; };
   const int4 sh = make_int4(lg(p.up[0]), lg(p.up[1]), lg(p.up[2]), lg(p.up[3]));
   const int per_row = p.W * c8n;
+  const int row_bytes = p.W * p.C * (int)dtype_size(p.base_dt);
+  static const bool no_pipe = [] { const char* e = getenv("B200ROMP_SUM_SIMPLE"); return e && e[0] == '1'; }();
+  if (!no_pipe && row_bytes % 16 == 0 && row_bytes <= 16384 && (reinterpret_cast<uintptr_t>(p.base) & 15) == 0 && per_row >= 128) {
+    const int smem = kSumStages * row_bytes + 2 * kSumStages * 8 + 128;
+    static bool attr_done = false;
+    if (!attr_done) {
+      B2R_CUDA_OK(cudaFuncSetAttribute(fuse_sum_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 16384 + 256));
+      attr_done = true;
+    }
+    const int blocks_per_sm = row_bytes <= 8192 ? 4 : 3;
+    const int grid = std::min(p.B * p.H, 148 * blocks_per_sm);
+    fuse_sum_pipe_kernel<<<grid, 256, smem, stream>>>(p, c8n, sh, row_bytes);
+    B2R_CUDA_OK(cudaGetLastError());
+    return B200ROMP_OK;
+  }
   const int threads = per_row >= 256 ? 256 : (per_row + 31) / 32 * 32;
   dim3 grid((per_row + threads - 1) / threads, std::min(p.B * p.H, 65535));
   fuse_sum_kernel<<<grid, threads, 0, stream>>>(p, c8n, sh);

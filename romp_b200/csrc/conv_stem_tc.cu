@@ -8,14 +8,16 @@
 // weights carry the factor 2/255, so  sum w*(2/255)*(x-127.5) = sum w*(x/255*2-1)  and zero padding stays zero; the only
 // rounding is the bf16 rounding of the scaled weights (same as every other layer on this engine).
 // Everything after the MMA is the shared TMA epilogue (tc_device.cuh): bias + ReLU + bf16, staged, tensor store.
-// Warp roles (kTcThreads): warps 0-1 producers (2 rows per thread), warp 2 TMEM allocator + MMA issuer, warps 3-10 epilogue.
+// Warp roles (416 threads): warps 0, 1, 11, 12 producers - each builds whole tiles in its private stage, so four gathers
+// (one DRAM latency each) are in flight per SM; warp 2 TMEM allocator + MMA issuer; warps 3-10 the shared epilogue.
 #include "conv_tc.cuh"
 #include "tc_device.cuh"
 
 namespace b200romp {
 
 namespace {
-constexpr int kStemStages = 4;
+constexpr int kStemStages = 4;                   // = producer warps, stage w is private to producer w
+constexpr int kStemThreads = kTcThreads + 64;    // two extra producer warps after the epilogue warps
 constexpr int kStemK = 32;                       // 27 padded to two UMMA_K steps
 constexpr int kStemRowB = kStemK * 2;            // 64 B rows -> SWIZZLE_64B
 constexpr int kStemABytes = 128 * kStemRowB;     // 8 KB per stage
@@ -25,7 +27,7 @@ constexpr int kStemAcc = AccCfg<1>::ACC;
 constexpr uint32_t kStemIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kStemNT >> 3) << 17) | ((128u >> 4) << 24);
 }  // namespace
 
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kStemThreads, 1)
 conv_stem_tc_kernel(const __grid_constant__ TcEpiMaps epi_maps, const ConvParams p, const uint8_t* __restrict__ wpack,
                     int tiles_x, int tiles_y, int num_tiles) {
   extern __shared__ uint8_t smem_raw[];
@@ -45,7 +47,7 @@ conv_stem_tc_kernel(const __grid_constant__ TcEpiMaps epi_maps, const ConvParams
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStemStages; ++i) {
-      mbar_init(&full[i], 2);                    // one arrival per producer warp
+      mbar_init(&full[i], 1);                    // its producer warp
       mbar_init(&empty[i], 1);
     }
     mbar_init(b_full, 1);
@@ -66,24 +68,24 @@ conv_stem_tc_kernel(const __grid_constant__ TcEpiMaps epi_maps, const ConvParams
   const int per_frame = tiles_x * tiles_y;
   pdl_trigger();
 
-  if (warp < 2) {
+  if (warp < 2 || warp >= kFirstEpiWarp + kEpiWarps) {
     // ===================== im2col producers =====================
+    const int pw = warp < 2 ? warp : warp - (kFirstEpiWarp + kEpiWarps) + 2;   // 0..3 = private stage
     if (threadIdx.x == 0) {
       mbar_arrive_expect_tx(b_full, kStemBBytes);
       bulk_copy_g2s(sB, wpack, kStemBBytes, b_full);
     }
     pdl_wait();                                  // frames may be produced by a predecessor kernel / copy
     const uint8_t* in = reinterpret_cast<const uint8_t*>(p.in);
-    int stage = 0;
+    uint8_t* a = sA + pw * kStemABytes;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x + pw * gridDim.x; tile < num_tiles; tile += kStemStages * gridDim.x) {
       const int n = tile / per_frame, rem = tile % per_frame;
       const int y0 = (rem / tiles_x) * 16, x0 = (rem % tiles_x) * 8;
-      mbar_wait(&empty[stage], phase ^ 1);
-      uint8_t* a = sA + stage * kStemABytes;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int m = half * 64 + threadIdx.x;             // A row = TMEM lane = pixel (m >> 3, m & 7) of the tile
+      mbar_wait(&empty[pw], phase ^ 1);
+#pragma unroll 2
+      for (int j = 0; j < 4; ++j) {
+        const int m = j * 32 + lane;                       // A row = TMEM lane = pixel (m >> 3, m & 7) of the tile
         const int oy = y0 + (m >> 3), ox = x0 + (m & 7);
         uint32_t w[16];                                    // 32 bf16, k = r*9 + s*3 + c
         float v[32];
@@ -108,13 +110,13 @@ conv_stem_tc_kernel(const __grid_constant__ TcEpiMaps epi_maps, const ConvParams
           w[k] = *reinterpret_cast<uint32_t*>(&h);
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j)                        // 16 B chunk j of row m, Swizzle<2,4,3>
-          *reinterpret_cast<uint4*>(a + m * kStemRowB + ((j ^ ((m >> 1) & 3)) * 16)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+        for (int q4 = 0; q4 < 4; ++q4)                     // 16 B chunk q4 of row m, Swizzle<2,4,3>
+          *reinterpret_cast<uint4*>(a + m * kStemRowB + ((q4 ^ ((m >> 1) & 3)) * 16)) = make_uint4(w[4 * q4], w[4 * q4 + 1], w[4 * q4 + 2], w[4 * q4 + 3]);
       }
       fence_proxy_async();                                 // generic-proxy writes -> visible to the tensor core
       __syncwarp();
-      if (lane == 0) mbar_arrive(&full[stage]);
-      if (++stage == kStemStages) { stage = 0; phase ^= 1; }
+      if (lane == 0) mbar_arrive(&full[pw]);
+      phase ^= 1;
     }
   } else if (warp == 2) {
     // ===================== MMA issuer =====================
@@ -191,7 +193,7 @@ int tc_stem_launch(const TcConvPlan& plan, const ConvParams& p, cudaStream_t str
   const int tiles_x = p.Wout / 8, tiles_y = p.Hout / 16;
   const int num_tiles = tiles_x * tiles_y * p.B;
   dim3 grid(std::min(plan.grid_x, num_tiles), 1);
-  B2R_CUDA_OK(tc_launch(conv_stem_tc_kernel, grid, plan.smem_bytes, stream, em, p, reinterpret_cast<const uint8_t*>(plan.d_wpack),
+  B2R_CUDA_OK(tc_launch(conv_stem_tc_kernel, grid, kStemThreads, plan.smem_bytes, stream, em, p, reinterpret_cast<const uint8_t*>(plan.d_wpack),
                         tiles_x, tiles_y, num_tiles));
   return B200ROMP_OK;
 }

@@ -202,7 +202,7 @@ static int s2_inst(const TcConvPlan& plan, const ConvParams& p, cudaStream_t str
   const int tiles_x = p.Wout / 8, tiles_y = p.Hout / 16;
   const int num_tiles = tiles_x * tiles_y * p.B;
   dim3 grid(std::min(plan.grid_x, num_tiles), plan.grid_y);
-  B2R_CUDA_OK(tc_launch(kern, grid, plan.smem_bytes, stream, maps, em, p, reinterpret_cast<const uint8_t*>(plan.d_wpack), tiles_x,
+  B2R_CUDA_OK(tc_launch(kern, grid, kTcThreads, plan.smem_bytes, stream, maps, em, p, reinterpret_cast<const uint8_t*>(plan.d_wpack), tiles_x,
                         tiles_y, num_tiles, plan.stages, KSPLIT == 1 ? plan.tma_epi : 0));
   return B200ROMP_OK;
 }

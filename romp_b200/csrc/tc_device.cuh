@@ -395,11 +395,11 @@ __device__ __forceinline__ void tc_epilogue_loop_tma(const ConvParams& p, const 
 
 // launch with the programmatic-stream-serialization attribute (see pdl_trigger / pdl_wait); B200ROMP_NO_PDL=1 disables it
 template <typename... KArgs, typename... Args>
-static inline cudaError_t tc_launch(void (*kern)(KArgs...), dim3 grid, int smem_bytes, cudaStream_t stream, Args&&... args) {
+static inline cudaError_t tc_launch(void (*kern)(KArgs...), dim3 grid, int threads, int smem_bytes, cudaStream_t stream, Args&&... args) {
   static const bool pdl = [] { const char* e = getenv("B200ROMP_NO_PDL"); return !(e && e[0] == '1'); }();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
-  cfg.blockDim = dim3(kTcThreads);
+  cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = (size_t)smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute at[1];
