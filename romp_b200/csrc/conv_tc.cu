@@ -31,7 +31,9 @@ template <int KS, int CIN, int NT, bool PER_TAP, int KSPLIT>
 struct TcCfg {
   static constexpr int TAPS = KS * KS;
   static constexpr int PAD = KS / 2;
-  static constexpr int CW = CIN < 64 ? CIN : 64;       // channels per chunk = one swizzle row
+  // channels per chunk = one swizzle row.  The weight-heavy 3x3 layers (Cin >= 128: 147 KB resident weights) use half
+  // chunks: 4-5 stages of 12 KB instead of 2 of 23 KB, so loads run ahead of the MMAs
+  static constexpr int CW = tc_chunk_width(KS, CIN);
   static constexpr int KCH = CIN / CW;
   static constexpr int ROWB = CW * 2;                  // bytes per pixel row in smem (64 or 128)
   static constexpr int LAYOUT = ROWB == 128 ? 2 : 4;   // SWIZZLE_128B / SWIZZLE_64B
@@ -90,7 +92,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   const uint32_t tmem_base = *tmem_ptr;
   pdl_trigger();
   const int per_frame = tiles_x * tiles_y;
-  const int nrings = stages >= 2 ? kMmaWarps : 1;   // MMA-issuing warps in use = private stage rings
+  const int nrings = tc_num_rings(stages);   // MMA-issuing warps in use = private stage rings
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -201,8 +203,8 @@ PFN_encodeTiled tc_get_encode() {
   return fn;
 }
 
-int tc_pack_weights(const float* w_oihw, int cin, int cout, int taps, int nt, void** d_out, std::vector<void*>* allocs) {
-  const int cw = cin < 64 ? cin : 64, kch = cin / cw, rowb = cw * 2, ntiles = (cout + nt - 1) / nt;
+int tc_pack_weights(const float* w_oihw, int cin, int cout, int taps, int nt, void** d_out, std::vector<void*>* allocs, int cw_in) {
+  const int cw = cw_in > 0 ? cw_in : (cin < 64 ? cin : 64), kch = cin / cw, rowb = cw * 2, ntiles = (cout + nt - 1) / nt;
   std::vector<__nv_bfloat16> img((size_t)ntiles * taps * kch * nt * cw, __float2bfloat16_rn(0.f));
   for (int j = 0; j < ntiles; ++j)
     for (int t = 0; t < taps; ++t)
@@ -330,7 +332,7 @@ int tc_conv_prepare(const ConvParams& p, int ksize, int stride, const float* w_o
   const bool per_tap = false;   // the per-tap TMA variant (PER_TAP=true) was only the bring-up fallback
   { const char* e = getenv("B200ROMP_TC_KSPLIT"); plan->ksplit = (e && e[0] == '4') ? 0 : 1; }   /* K-split measured slower: off by default */
   const int taps = ksize * ksize;
-  const int cw = p.cin < 64 ? p.cin : 64, kch = p.cin / cw, rowb = cw * 2;
+  const int cw = tc_chunk_width(ksize, p.cin), kch = p.cin / cw, rowb = cw * 2;
   // N tile: weights must stay resident next to >= 2 pipeline stages
   int nt = (p.cout % 64 == 0) ? 64 : 32;
   const int hh = per_tap ? 16 : 16 + 2 * (ksize / 2), hw = per_tap ? 8 : 8 + 2 * (ksize / 2);
@@ -362,7 +364,7 @@ int tc_conv_prepare(const ConvParams& p, int ksize, int stride, const float* w_o
   plan->grid_y = (p.cout + nt - 1) / nt;
   plan->grid_x = std::max(1, sm_count / plan->grid_y);
   plan->smem_bytes = bbytes(nt) + stages * stage_bytes + epi_bytes + 1024 + 1024;
-  int rcw = tc_pack_weights(w_oihw, p.cin, p.cout, taps, nt, &plan->d_wpack, allocs);
+  int rcw = tc_pack_weights(w_oihw, p.cin, p.cout, taps, nt, &plan->d_wpack, allocs, cw);
   if (rcw) return rcw;
   // ---- tensor map over the NHWC input: dims (C slice, W, H, N), halo box, OOB -> zeros
   CUtensorMap tm;

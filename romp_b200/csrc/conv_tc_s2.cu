@@ -88,7 +88,7 @@ conv_tc_s2_kernel(const __grid_constant__ S2Maps maps, const __grid_constant__ T
   const uint32_t tmem_base = *tmem_ptr;
   pdl_trigger();
   const int per_frame = tiles_x * tiles_y;
-  const int nrings = stages >= 2 ? kMmaWarps : 1;   // MMA-issuing warps in use = private stage rings
+  const int nrings = tc_num_rings(stages);   // MMA-issuing warps in use = private stage rings
 
   if (warp == 0) {
     if (elect_one()) {

@@ -200,7 +200,11 @@ constexpr int kMmaWarps = 2;         // two MMA-issuing warps alternate tiles: o
 constexpr int kFirstEpiWarp = 1 + kMmaWarps;
 // the smem stages are split into one private ring per MMA warp: ring 0 gets the larger half
 // (a single stage cannot be split: then only the first MMA warp works and owns it)
-__host__ __device__ constexpr int tc_ring_size(int stages, int ring) { return stages < 2 ? stages : (stages + 1 - ring) / 2; }
+// With fewer than 4 stages (weight-heavy layers: Cin >= 128) a split would leave one stage per ring, i.e. no overlap of a
+// ring's TMA load with its MMAs (measured: 128->128@32x32 29 us); then one MMA warp owns all stages.
+__host__ __device__ constexpr int tc_chunk_width(int ksize, int cin) { return (ksize == 3 && cin >= 128) ? 32 : (cin < 64 ? cin : 64); }
+__host__ __device__ constexpr int tc_num_rings(int stages) { return stages >= 4 ? kMmaWarps : 1; }
+__host__ __device__ constexpr int tc_ring_size(int stages, int ring) { return tc_num_rings(stages) == 1 ? stages : (stages + 1 - ring) / 2; }
 __host__ __device__ constexpr int tc_ring_base(int stages, int ring) { return ring ? (stages + 1) / 2 : 0; }
 constexpr int kTcThreads = (kFirstEpiWarp + kEpiWarps) * 32;
 
@@ -417,7 +421,7 @@ PFN_encodeTiled tc_get_encode();
 // decides whether the TMA epilogue applies (sets plan->tma_epi and the out/res tensor maps); 0 = direct epilogue
 int tc_epi_prepare(const ConvParams& p, int nt, bool ptrs_final, TcConvPlan* plan);
 // bf16 weight slab in shared-memory-image order [ntile][tap][chunk][NT rows x ROWB] with the TMA/UMMA XOR swizzle
-int tc_pack_weights(const float* w_oihw, int cin, int cout, int taps, int nt, void** d_out, std::vector<void*>* allocs);
+int tc_pack_weights(const float* w_oihw, int cin, int cout, int taps, int nt, void** d_out, std::vector<void*>* allocs, int cw = 0);
 // stride-2 3x3 engine (conv_tc_s2.cu)
 bool tc_s2_supported(const ConvParams& p);
 int tc_s2_prepare(const ConvParams& p, const float* w_oihw, int sm_count, bool ptrs_final, TcConvPlan* plan, std::vector<void*>* allocs);
