@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "lib", "libb200romp.so")
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["net.cu", "conv_simt.cu", "conv_tc.cu", "conv_tc_s2.cu", "conv_stem_tc.cu", "parse.cu", "smpl.cu", "project.cu", "bev.cu"]
+SOURCES = ["net.cu", "conv_simt.cu", "conv_tc.cu", "conv_tc_s2.cu", "conv_stem_tc.cu", "conv_tc_2cta.cu", "parse.cu", "smpl.cu", "project.cu", "bev.cu"]
 
 F32, BF16, U8 = 0, 1, 2
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2

@@ -324,6 +324,10 @@ int tc_epi_prepare(const ConvParams& p, int nt, bool ptrs_final, TcConvPlan* pla
 int tc_conv_prepare(const ConvParams& p, int ksize, int stride, const float* w_oihw, int sm_count, bool ptrs_final, TcConvPlan* plan,
                     std::vector<void*>* allocs) {
   if (stride == 2) return tc_s2_prepare(p, w_oihw, sm_count, ptrs_final, plan, allocs);
+  {
+    const int r2 = tc2_try_prepare(p, ksize, stride, w_oihw, sm_count, ptrs_final, plan, allocs);   // CTA pairs where they apply
+    if (r2 != 0) return r2 < 0 ? r2 : B200ROMP_OK;
+  }
   PFN_encodeTiled encode = tc_get_encode();
   if (!encode) {
     set_error("conv_tc: cuTensorMapEncodeTiled is unavailable");
@@ -386,6 +390,7 @@ int tc_conv_prepare(const ConvParams& p, int ksize, int stride, const float* w_o
 
 int tc_conv_launch(const TcConvPlan& plan, const ConvParams& p, cudaStream_t stream) {
   if (plan.kind == 33) return tc_stem_launch(plan, p, stream);
+  if (plan.kind == 34) return tc2_launch(plan, p, stream);
   if (plan.kind % 10 == 2) return tc_s2_launch(plan, p, stream);
   return dispatch<false>(plan, p, stream, false);
 }

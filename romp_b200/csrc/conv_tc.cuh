@@ -28,6 +28,10 @@ bool tc_conv_supported(const ConvParams& p, int ksize, int stride);
 int tc_conv_prepare(const ConvParams& p, int ksize, int stride, const float* w_oihw, int sm_count, bool ptrs_final, TcConvPlan* plan,
                     std::vector<void*>* allocs);
 int tc_conv_launch(const TcConvPlan& plan, const ConvParams& p, cudaStream_t stream);
+// CTA-pair engine for 3x3 stride-1 convs (conv_tc_2cta.cu): 1 = plan filled, 0 = not applicable, < 0 = error
+int tc2_try_prepare(const ConvParams& p, int ksize, int stride, const float* w_oihw, int sm_count, bool ptrs_final, TcConvPlan* plan,
+                    std::vector<void*>* allocs);
+int tc2_launch(const TcConvPlan& plan, const ConvParams& p, cudaStream_t stream);
 // stem engine (conv_stem_tc.cu): 3->64 3x3 stride-2 conv on raw u8 frames with the input normalisation folded in
 bool tc_stem_supported(const ConvParams& p, int ksize, int stride);
 int tc_stem_prepare(const ConvParams& p, const float* w_oihw, int sm_count, bool out_final, TcConvPlan* plan,

@@ -1,0 +1,301 @@
+// tcgen05 3x3 stride-1 implicit-GEMM conv on CTA PAIRS (cta_group::2): one tcgen05.mma covers M = 256 pixels - the 16x8
+// tiles of the two CTAs of a 2-CTA cluster - so the per-instruction issue cost (the limiter of the N <= 64 layers, see
+// DESIGN 4.1) is paid once per two SMs, and each CTA keeps only HALF of the weight slab (its N/2 rows of every B tile),
+// which frees shared memory for pipeline stages on the Cin >= 128 layers.
+//
+// Everything else is conv_tc.cu's design: halo tile by TMA + 9 shifted descriptors, persistent tile loop, two MMA warps
+// with private stage rings, TMEM accumulator ring, the TMA epilogue.  Pair protocol (PTX ISA cta_group::2 / CUTLASS sm100):
+//   * CTA rank 0 of the cluster is the leader: only its MMA warps issue.  Tile it of CTA r is blockIdx.x + it*gridDim.x,
+//     so the pair (2c, 2c+1) always works on two adjacent tiles.
+//   * A: each CTA TMA-loads its own halo tile into its own smem with the .cta_group::2 form whose mbarrier operand has
+//     the peer bit cleared: both loads complete_tx on the LEADER's full[stage]; the leader's producer posts
+//     expect_tx(2 x payload).  Each producer paces itself on its own empty[stage].
+//   * B: CTA r holds rows [r*N/2, (r+1)*N/2) of every (tap, chunk) weight tile; the peer tells the leader when its
+//     slab has landed by a remote arrive on b_peer.
+//   * tcgen05.commit.cta_group::2 with multicast mask 0b11 arrives on empty[stage] / tmem_full[acc] of BOTH CTAs.
+//   * D: rows 0-127 of the 256-row accumulator live in the leader's TMEM, rows 128-255 in the peer's, same columns; each
+//     CTA's epilogue drains its own TMEM and arrives (remotely for the peer) on the leader's tmem_empty[acc] (count 8).
+#include <mutex>
+
+#include "conv_tc.cuh"
+#include "tc_device.cuh"
+
+namespace b200romp {
+
+template <int CIN, int NT>
+struct Tc2Cfg {
+  static constexpr int KS = 3, TAPS = 9, PAD = 1;
+  static constexpr int CW = tc_chunk_width(3, CIN);
+  static constexpr int KCH = CIN / CW;
+  static constexpr int ROWB = CW * 2;
+  static constexpr int LAYOUT = ROWB == 128 ? 2 : 4;
+  static constexpr int HW_ = 10, HH = 18;
+  static constexpr int STAGE_PAYLOAD = HH * HW_ * ROWB;
+  static constexpr int STAGE_BYTES = (STAGE_PAYLOAD + 1023) / 1024 * 1024;
+  static constexpr int BTILE = (NT / 2) * ROWB;               // this CTA's half of one (tap, chunk) weight tile
+  static constexpr int B_BYTES = TAPS * KCH * BTILE;
+  static constexpr int ACC = AccCfg<1>::ACC;
+  static constexpr int TMEM_COLS = tc_tmem_cols(ACC * NT);
+  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((256u >> 4) << 24);
+};
+
+template <int CIN, int NT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcEpiMaps epi_maps, const ConvParams p,
+                const uint8_t* __restrict__ wpack, int tiles_x, int tiles_y, int num_tiles, int stages, int tma_epi) {
+  using Cfg = Tc2Cfg<CIN, NT>;
+  constexpr int kAccStages = Cfg::ACC;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sB = smem;
+  uint8_t* sA = smem + (Cfg::B_BYTES + 1023) / 1024 * 1024;
+  uint8_t* epi_smem = sA + (size_t)stages * Cfg::STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(epi_smem + tc_epi_total_bytes(tma_epi, NT));
+  uint64_t* empty = full + stages;
+  uint64_t* b_full = empty + stages;
+  uint64_t* b_peer = b_full + 1;
+  uint64_t* tmem_full = b_peer + 1;
+  uint64_t* tmem_empty = tmem_full + kAccStages;
+  uint64_t* res_bar = tmem_empty + kAccStages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 2 * kEpiWarps);
+  float* s_bias = reinterpret_cast<float*>(tmem_ptr + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const uint32_t rank = cluster_ctarank();          // 0 = leader
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(b_full, 1);
+    mbar_init(b_peer, 1);
+    for (int i = 0; i < kAccStages; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 8);                 // 4 epilogue warps of each CTA of the pair
+    }
+    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
+    fence_barrier_init();
+  }
+  if (threadIdx.x >= kFirstEpiWarp * 32 && threadIdx.x < kFirstEpiWarp * 32 + NT)
+    s_bias[threadIdx.x - kFirstEpiWarp * 32] = p.bias[blockIdx.y * NT + threadIdx.x - kFirstEpiWarp * 32];
+  if (warp == 1) tmem_alloc_2cta(tmem_ptr, Cfg::TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();                               // barriers of both CTAs initialised before any remote arrive / TMA credit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int per_frame = tiles_x * tiles_y;
+  const int nrings = tc_num_rings(stages);
+  pdl_trigger();
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (elect_one()) {
+      mbar_arrive_expect_tx(b_full, Cfg::B_BYTES);
+      const uint8_t* wsrc = wpack + ((size_t)blockIdx.y * 2 + rank) * Cfg::B_BYTES;
+      for (int i = 0; i < Cfg::TAPS * Cfg::KCH; ++i)
+        bulk_copy_g2s(sB + (size_t)i * Cfg::BTILE, wsrc + (size_t)i * Cfg::BTILE, Cfg::BTILE, b_full);
+      pdl_wait();
+      int stage = 0, stage_other = 0;
+      uint32_t phase = 0, phase_other = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int n = tile / per_frame, rem = tile % per_frame;
+        const int y0 = (rem / tiles_x) * 16, x0 = (rem % tiles_x) * 8;
+        const int ring = nrings == 2 ? (it & 1) : 0, rbase = tc_ring_base(stages, ring), rsize = tc_ring_size(stages, ring);
+        for (int c = 0; c < Cfg::KCH; ++c) {
+          const int sidx = rbase + stage;
+          mbar_wait(&empty[sidx], phase ^ 1);
+          if (rank == 0) mbar_arrive_expect_tx(&full[sidx], 2 * Cfg::STAGE_PAYLOAD);      // own tile + the peer's
+          tma_load_4d_2cta(sA + (size_t)sidx * Cfg::STAGE_BYTES, &tmap, &full[sidx], c * Cfg::CW, x0 - 1, y0 - 1, n);
+          if (++stage == rsize) { stage = 0; phase ^= 1; }
+        }
+        if (nrings == 2) { const int ts = stage; stage = stage_other; stage_other = ts; const uint32_t tp = phase; phase = phase_other; phase_other = tp; }
+      }
+    }
+  } else if (warp <= kMmaWarps) {
+    if (rank != 0) {
+      // peer: report "weight slab resident" to the leader, nothing else to do
+      if (warp == 1 && elect_one()) {
+        mbar_wait(b_full, 0);
+        mbar_arrive_cluster(b_peer, 0);
+      }
+    } else if (warp <= nrings && elect_one()) {
+      // ===================== MMA issuers (leader CTA only) =====================
+      mbar_wait(b_full, 0);
+      mbar_wait(b_peer, 0);
+      tc_fence_after();
+      const uint32_t b_base = smem_u32(sB);
+      const int rbase = tc_ring_base(stages, warp - 1), rsize = tc_ring_size(stages, warp - 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = warp - 1;
+      for (int tile = blockIdx.x + it * gridDim.x; tile < num_tiles; tile += nrings * gridDim.x, it += nrings) {
+        const int acc = it & (kAccStages - 1);
+        mbar_wait(&tmem_empty[acc], ((it / kAccStages) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tile = tmem_base + (uint32_t)(acc * NT);
+        int mma_i = 0;
+        for (int c = 0; c < Cfg::KCH; ++c) {
+          const int sidx = rbase + stage;
+          mbar_wait(&full[sidx], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + (size_t)sidx * Cfg::STAGE_BYTES);
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const int r = t / 3, s = t % 3;
+            const uint32_t a_tap = a_base + (uint32_t)((r * Cfg::HW_ + s) * Cfg::ROWB);
+            const uint32_t b_tap = b_base + (uint32_t)((t * Cfg::KCH + c) * Cfg::BTILE);
+#pragma unroll
+            for (int k = 0; k < Cfg::CW / 16; ++k) {
+              const uint64_t adesc = make_smem_desc(a_tap + k * 32, Cfg::HW_ * Cfg::ROWB, Cfg::LAYOUT);
+              const uint64_t bdesc = make_smem_desc(b_tap + k * 32, 8 * Cfg::ROWB, Cfg::LAYOUT);
+              umma_bf16_2cta(d_tile, adesc, bdesc, Cfg::IDESC, mma_i > 0 ? 1u : 0u);
+              ++mma_i;
+            }
+          }
+          umma_commit_2cta(&empty[sidx]);          // both CTAs' stage buffers are reusable once these MMAs retire
+          if (++stage == rsize) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2cta(&tmem_full[acc]);         // both halves of the accumulator complete -> both epilogues
+      }
+    }
+  } else {
+    tc_epilogue_loop_tma<NT, true>(p, epi_maps, tma_epi, epi_smem, res_bar, tmem_base, tmem_full, tmem_empty, s_bias, tiles_x,
+                                   per_frame, num_tiles);
+  }
+  tc_fence_before();
+  cluster_sync_all();                               // no CTA leaves while its peer may still address its barriers / TMEM
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weights: [ntile][half][tap][chunk][NT/2 rows x ROWB], swizzled by the row index inside the half tile
+static int pack_weights_2cta(const float* w_oihw, int cin, int cout, int nt, int cw, void** d_out, std::vector<void*>* allocs) {
+  const int kch = cin / cw, rowb = cw * 2, ntiles = cout / nt, hn = nt / 2;
+  std::vector<__nv_bfloat16> img((size_t)ntiles * 2 * 9 * kch * hn * cw, __float2bfloat16_rn(0.f));
+  for (int j = 0; j < ntiles; ++j)
+    for (int h = 0; h < 2; ++h)
+      for (int t = 0; t < 9; ++t)
+        for (int c = 0; c < kch; ++c) {
+          __nv_bfloat16* tile = img.data() + ((((size_t)j * 2 + h) * 9 + t) * kch + c) * hn * cw;
+          for (int n = 0; n < hn; ++n)
+            for (int k = 0; k < cw; ++k) {
+              const int co = j * nt + h * hn + n, ci = c * cw + k;
+              const float w = w_oihw[((size_t)co * cin + ci) * 9 + t];
+              const int chunk16 = k / 8;
+              const int phase = rowb == 128 ? (n & 7) : ((n >> 1) & 3);
+              const size_t byte = (size_t)n * rowb + (size_t)((chunk16 ^ phase) * 16) + (k % 8) * 2;
+              tile[byte / 2] = __float2bfloat16_rn(w);
+            }
+        }
+  B2R_CUDA_OK(cudaMalloc(d_out, img.size() * sizeof(__nv_bfloat16)));
+  allocs->push_back(*d_out);
+  B2R_CUDA_OK(cudaMemcpy(*d_out, img.data(), img.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+  return B200ROMP_OK;
+}
+
+template <int CIN, int NT>
+static int tc2_inst(const TcConvPlan& plan, const ConvParams& p, cudaStream_t stream, bool attr) {
+  auto kern = conv_tc2_kernel<CIN, NT>;
+  if (attr) {
+    B2R_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    return B200ROMP_OK;
+  }
+  CUtensorMap tm;
+  memcpy(&tm, plan.tmap_in, sizeof(tm));
+  TcEpiMaps em;
+  memcpy(&em, plan.tmap_epi, sizeof(em));
+  const int tiles_x = p.Wout / 8, tiles_y = p.Hout / 16;
+  const int num_tiles = tiles_x * tiles_y * p.B;
+  dim3 grid(std::min(plan.grid_x, num_tiles) & ~1, plan.grid_y);
+  static const bool pdl = [] { const char* e = getenv("B200ROMP_NO_PDL"); return !(e && e[0] == '1'); }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = (size_t)plan.smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 2 : 1;
+  B2R_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tm, em, p, reinterpret_cast<const uint8_t*>(plan.d_wpack), tiles_x, tiles_y, num_tiles,
+                                 plan.stages, plan.tma_epi));
+  return B200ROMP_OK;
+}
+
+static int tc2_dispatch(const TcConvPlan& plan, const ConvParams& p, cudaStream_t stream, bool attr) {
+#define B2R_C2(C, N) \
+  if (plan.cin == C && plan.nt == N) return tc2_inst<C, N>(plan, p, stream, attr);
+  B2R_C2(32, 32) B2R_C2(64, 64) B2R_C2(128, 64) B2R_C2(256, 64) B2R_C2(256, 32) B2R_C2(32, 64)
+#undef B2R_C2
+  set_error("conv_tc_2cta: no instantiation for cin%d nt%d", plan.cin, plan.nt);
+  return B200ROMP_EINVAL;
+}
+
+// Decides whether the CTA-pair engine applies and, if so, fills the plan (kind 34).  Returns 1 = taken, 0 = not
+// applicable (caller continues with the single-CTA plan), < 0 = error.
+int tc2_try_prepare(const ConvParams& p, int ksize, int stride, const float* w_oihw, int sm_count, bool ptrs_final, TcConvPlan* plan,
+                    std::vector<void*>* allocs) {
+  static const bool off = [] { const char* e = getenv("B200ROMP_TC_NO_2CTA"); return e && e[0] == '1'; }();
+  if (off || ksize != 3 || stride != 1 || !ptrs_final) return 0;
+  if (p.cin != 32 && p.cin != 64 && p.cin != 128 && p.cin != 256) return 0;
+  if (p.cout % 32 != 0) return 0;
+  const int tiles = (p.Wout / 8) * (p.Hout / 16);
+  if (tiles % 2 != 0) return 0;                                        // pairs must never split across the tail
+  PFN_encodeTiled encode = tc_get_encode();
+  if (!encode) return 0;
+  const int cw = tc_chunk_width(3, p.cin), kch = p.cin / cw, rowb = cw * 2;
+  int nt = (p.cout % 64 == 0) ? 64 : 32;
+  const int stage_bytes = (18 * 10 * rowb + 1023) / 1024 * 1024;
+  const int budget = 227 * 1024 - 1024 - 1024;
+  auto bbytes = [&](int n) { return (9 * kch * (n / 2) * rowb + 1023) / 1024 * 1024; };
+  plan->ksplit = 1;
+  if (!tc_epi_prepare(p, nt, ptrs_final, plan)) return 0;               // the pair engine only has the TMA epilogue
+  int epi_bytes = tc_epi_total_bytes(plan->tma_epi, nt);
+  if (bbytes(nt) + 4 * stage_bytes + epi_bytes > budget && nt == 64 && p.cout % 64 == 0 && p.cin == 256) {
+    // 256 -> 256: NT = 64 leaves too few stages; fall back to NT = 32 tiles
+    nt = 32;
+    if (!tc_epi_prepare(p, nt, ptrs_final, plan)) return 0;
+    epi_bytes = tc_epi_total_bytes(plan->tma_epi, nt);
+  }
+  if (bbytes(nt) + 2 * stage_bytes + epi_bytes > budget) return 0;
+  const int dbl = tc_epi_total_bytes(plan->tma_epi | kTmaEpiDouble, nt);
+  if ((plan->tma_epi & kTmaEpiRes) && (budget - bbytes(nt) - dbl) / stage_bytes >= 6) {
+    plan->tma_epi |= kTmaEpiDouble;
+    epi_bytes = dbl;
+  }
+  int stages = std::min(8, (budget - bbytes(nt) - epi_bytes) / stage_bytes);
+  plan->kind = 34;
+  plan->cin = p.cin; plan->cout = p.cout; plan->nt = nt; plan->stages = stages;
+  plan->grid_y = p.cout / nt;
+  plan->grid_x = std::max(2, (sm_count / plan->grid_y) & ~1);
+  plan->smem_bytes = bbytes(nt) + stages * stage_bytes + epi_bytes + 1024 + 1024;
+  int rc = pack_weights_2cta(w_oihw, p.cin, p.cout, nt, cw, &plan->d_wpack, allocs);
+  if (rc) return rc;
+  CUtensorMap tm;
+  const cuuint64_t gdim[4] = {(cuuint64_t)p.cin, (cuuint64_t)p.Win, (cuuint64_t)p.Hin, (cuuint64_t)p.B};
+  const cuuint64_t gstr[3] = {(cuuint64_t)p.in_C * 2, (cuuint64_t)p.Win * p.in_C * 2, (cuuint64_t)p.Hin * p.Win * p.in_C * 2};
+  const cuuint32_t box[4] = {(cuuint32_t)cw, 10, 18, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const void* base = reinterpret_cast<const __nv_bfloat16*>(p.in) + p.in_c_off;
+  CUresult cr = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    set_error("conv_tc_2cta: cuTensorMapEncodeTiled failed with %d", (int)cr);
+    return B200ROMP_ECUDA;
+  }
+  memcpy(plan->tmap_in, &tm, sizeof(tm));
+  rc = tc2_dispatch(*plan, p, nullptr, true);
+  return rc ? rc : 1;
+}
+
+int tc2_launch(const TcConvPlan& plan, const ConvParams& p, cudaStream_t stream) { return tc2_dispatch(plan, p, stream, false); }
+
+}  // namespace b200romp
