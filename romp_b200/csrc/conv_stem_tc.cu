@@ -27,6 +27,7 @@ constexpr int kStemABytes = 128 * kStemRowB;     // 8 KB per stage
 constexpr int kStemNT = 64;
 constexpr int kStemBBytes = kStemNT * kStemRowB; // 4 KB weight image
 constexpr int kStemAcc = AccCfg<1>::ACC;
+constexpr int kStemEpi = tc_epi_with_nbuf(kTmaEpiOut, 2);   // TMA epilogue, two staging tiles per warp
 constexpr int kRawRowB = 80;                     // bytes [6*x0 - 16, 6*x0 + 64) of each input row: 16 B aligned, covers ix = 2*x0-1 .. 2*x0+15
 constexpr int kRawRows = 33;                     // iy = 2*y0 - 1 .. 2*y0 + 31
 constexpr int kRawBytes = kRawRows * kRawRowB;   // 2640 B per window (TMA box)
@@ -44,14 +45,14 @@ conv_stem_tc_kernel(const __grid_constant__ CUtensorMap raw_map, const __grid_co
   uint8_t* sB = smem;
   uint8_t* sA = smem + kStemBBytes;
   uint8_t* epi_smem = sA + kStemStages * kStemABytes;
-  uint8_t* raw_smem = epi_smem + tc_epi_total_bytes(kTmaEpiOut, kStemNT);
+  uint8_t* raw_smem = epi_smem + tc_epi_total_bytes(kStemEpi, kStemNT);
   uint64_t* full = reinterpret_cast<uint64_t*>(raw_smem + kStemStages * kRawDepth * kRawStage);
   uint64_t* empty = full + kStemStages;
   uint64_t* b_full = empty + kStemStages;
   uint64_t* tmem_full = b_full + 1;
   uint64_t* tmem_empty = tmem_full + kStemAcc;
   uint64_t* res_bar = tmem_empty + kStemAcc;
-  uint64_t* raw_full = res_bar + 2 * kEpiWarps;
+  uint64_t* raw_full = res_bar + 3 * kEpiWarps;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(raw_full + kStemStages * kRawDepth);
   float* s_bias = reinterpret_cast<float*>(tmem_ptr + 2);
 
@@ -66,7 +67,7 @@ conv_stem_tc_kernel(const __grid_constant__ CUtensorMap raw_map, const __grid_co
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 4);
     }
-    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
+    for (int i = 0; i < 3 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
     for (int i = 0; i < kStemStages * kRawDepth; ++i) mbar_init(&raw_full[i], 1);
     fence_barrier_init();
   }
@@ -177,7 +178,7 @@ conv_stem_tc_kernel(const __grid_constant__ CUtensorMap raw_map, const __grid_co
       }
     }
   } else {
-    tc_epilogue_loop_tma<kStemNT>(p, epi_maps, kTmaEpiOut, epi_smem, res_bar, tmem_base, tmem_full, tmem_empty, s_bias, tiles_x,
+    tc_epilogue_loop_tma<kStemNT>(p, epi_maps, kStemEpi, epi_smem, res_bar, tmem_base, tmem_full, tmem_empty, s_bias, tiles_x,
                                   per_frame, num_tiles);
   }
   tc_fence_before();
@@ -216,7 +217,7 @@ int tc_stem_prepare(const ConvParams& p, const float* w_oihw, int sm_count, bool
   plan->kind = 33;
   plan->cin = 3; plan->cout = 64; plan->nt = kStemNT; plan->stages = kStemStages;
   plan->grid_x = sm_count; plan->grid_y = 1;
-  plan->smem_bytes = kStemBBytes + kStemStages * kStemABytes + tc_epi_total_bytes(kTmaEpiOut, kStemNT) +
+  plan->smem_bytes = kStemBBytes + kStemStages * kStemABytes + tc_epi_total_bytes(kStemEpi, kStemNT) +
                      kStemStages * kRawDepth * kRawStage + 2048;
   B2R_CUDA_OK(cudaFuncSetAttribute(conv_stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, plan->smem_bytes));
   return B200ROMP_OK;

@@ -66,7 +66,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   uint64_t* tmem_full = b_full + 1;
   uint64_t* tmem_empty = tmem_full + kAccStages;
   uint64_t* res_bar = tmem_empty + kAccStages;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 2 * kEpiWarps);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 3 * kEpiWarps);
   float* s_bias = reinterpret_cast<float*>(tmem_ptr + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -80,7 +80,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 4);
     }
-    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
+    for (int i = 0; i < 3 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (threadIdx.x >= kFirstEpiWarp * 32 && threadIdx.x < kFirstEpiWarp * 32 + NT)
@@ -351,14 +351,11 @@ int tc_conv_prepare(const ConvParams& p, int ksize, int stride, const float* w_o
   // TMA epilogue: needs kEpiWarps staging tiles next to >= 2 stages
   int epi_bytes = 0;
   if (tc_epi_prepare(p, nt, ptrs_final, plan)) {
-    epi_bytes = tc_epi_total_bytes(plan->tma_epi, nt);
-    if (bbytes(nt) + 2 * stage_bytes + epi_bytes > budget) { plan->tma_epi = 0; epi_bytes = 0; }
-    // residual double buffering where shared memory is plentiful (the Cin = Cout = 32 layers at 128x128, whose residual
-    // comes from HBM): measured 67.7 us with vs 46.1 us without residual on the single-buffered epilogue
-    const int dbl = tc_epi_total_bytes(plan->tma_epi | kTmaEpiDouble, nt);
-    if ((plan->tma_epi & kTmaEpiRes) && (budget - bbytes(nt) - dbl) / stage_bytes >= 6) {
-      plan->tma_epi |= kTmaEpiDouble;
-      epi_bytes = dbl;
+    const int nb = tc_epi_pick_nbuf(plan->tma_epi, nt, budget - bbytes(nt), stage_bytes);
+    if (nb == 0) plan->tma_epi = 0;
+    else {
+      plan->tma_epi = tc_epi_with_nbuf(plan->tma_epi, nb);
+      epi_bytes = tc_epi_total_bytes(plan->tma_epi, nt);
     }
   }
   int stages = (budget - bbytes(nt) - epi_bytes) / stage_bytes;

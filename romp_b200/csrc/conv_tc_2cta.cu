@@ -57,7 +57,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   uint64_t* tmem_full = b_peer + 1;
   uint64_t* tmem_empty = tmem_full + kAccStages;
   uint64_t* res_bar = tmem_empty + kAccStages;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 2 * kEpiWarps);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 3 * kEpiWarps);
   float* s_bias = reinterpret_cast<float*>(tmem_ptr + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -73,7 +73,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 8);                 // 4 epilogue warps of each CTA of the pair
     }
-    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
+    for (int i = 0; i < 3 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (threadIdx.x >= kFirstEpiWarp * 32 && threadIdx.x < kFirstEpiWarp * 32 + NT)
@@ -257,19 +257,10 @@ int tc2_try_prepare(const ConvParams& p, int ksize, int stride, const float* w_o
   auto bbytes = [&](int n) { return (9 * kch * (n / 2) * rowb + 1023) / 1024 * 1024; };
   plan->ksplit = 1;
   if (!tc_epi_prepare(p, nt, ptrs_final, plan)) return 0;               // the pair engine only has the TMA epilogue
-  int epi_bytes = tc_epi_total_bytes(plan->tma_epi, nt);
-  if (bbytes(nt) + 4 * stage_bytes + epi_bytes > budget && nt == 64 && p.cout % 64 == 0 && p.cin == 256) {
-    // 256 -> 256: NT = 64 leaves too few stages; fall back to NT = 32 tiles
-    nt = 32;
-    if (!tc_epi_prepare(p, nt, ptrs_final, plan)) return 0;
-    epi_bytes = tc_epi_total_bytes(plan->tma_epi, nt);
-  }
-  if (bbytes(nt) + 2 * stage_bytes + epi_bytes > budget) return 0;
-  const int dbl = tc_epi_total_bytes(plan->tma_epi | kTmaEpiDouble, nt);
-  if ((plan->tma_epi & kTmaEpiRes) && (budget - bbytes(nt) - dbl) / stage_bytes >= 6) {
-    plan->tma_epi |= kTmaEpiDouble;
-    epi_bytes = dbl;
-  }
+  const int nb = tc_epi_pick_nbuf(plan->tma_epi, nt, budget - bbytes(nt), stage_bytes);
+  if (nb == 0) return 0;
+  plan->tma_epi = tc_epi_with_nbuf(plan->tma_epi, nb);
+  const int epi_bytes = tc_epi_total_bytes(plan->tma_epi, nt);
   int stages = std::min(8, (budget - bbytes(nt) - epi_bytes) / stage_bytes);
   plan->kind = 34;
   plan->cin = p.cin; plan->cout = p.cout; plan->nt = nt; plan->stages = stages;

@@ -62,7 +62,7 @@ conv_tc_s2_kernel(const __grid_constant__ S2Maps maps, const __grid_constant__ T
   uint64_t* tmem_full = b_full + 1;
   uint64_t* tmem_empty = tmem_full + kAccStages;
   uint64_t* res_bar = tmem_empty + kAccStages;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 2 * kEpiWarps);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 3 * kEpiWarps);
   float* s_bias = reinterpret_cast<float*>(tmem_ptr + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -76,7 +76,7 @@ conv_tc_s2_kernel(const __grid_constant__ S2Maps maps, const __grid_constant__ T
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 4);
     }
-    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
+    for (int i = 0; i < 3 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (threadIdx.x >= kFirstEpiWarp * 32 && threadIdx.x < kFirstEpiWarp * 32 + NT)

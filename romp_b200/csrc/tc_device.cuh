@@ -80,6 +80,11 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
 }
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read(int pending) {   // at most `pending` (0..2) store groups may still be reading
+  if (pending <= 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  else if (pending == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+  else asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+}
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -339,10 +344,12 @@ __device__ __forceinline__ void tc_epilogue_loop(const ConvParams& p, uint32_t t
 struct TcEpiMaps {
   CUtensorMap out, res;
 };
-constexpr int kTmaEpiOut = 1, kTmaEpiRes = 2, kTmaEpiDouble = 4;
+constexpr int kTmaEpiOut = 1, kTmaEpiRes = 2, kTmaEpiBufShift = 2;   // bits 2-3: staging tiles per warp - 1
+__host__ __device__ constexpr int tc_epi_nbuf(int tma_epi) { return 1 + ((tma_epi >> kTmaEpiBufShift) & 3); }
+__host__ __device__ constexpr int tc_epi_with_nbuf(int tma_epi, int nbuf) { return (tma_epi & 3) | ((nbuf - 1) << kTmaEpiBufShift); }
 __host__ __device__ constexpr int tc_epi_stage_bytes(int nt) { return 32 * nt * 2; }   // per epilogue warp and buffer
 __host__ __device__ constexpr int tc_epi_total_bytes(int tma_epi, int nt) {
-  return tma_epi ? kEpiWarps * ((tma_epi & kTmaEpiDouble) ? 2 : 1) * tc_epi_stage_bytes(nt) : 0;
+  return tma_epi ? kEpiWarps * tc_epi_nbuf(tma_epi) * tc_epi_stage_bytes(nt) : 0;
 }
 
 template <int NT>
@@ -364,11 +371,14 @@ __device__ __forceinline__ void tc_epilogue_loop_tma(const ConvParams& p, const 
   const int q = warp & 3;
   const int co0 = blockIdx.y * NT;
   const bool has_res = (tma_epi & kTmaEpiRes) != 0;
-  // staging: one tile per warp, or two (kTmaEpiDouble) so that the residual of this warp's NEXT tile is already in
-  // flight while the current one is finished - hides the HBM latency of residuals that are not L2-resident
-  const int nbuf = (tma_epi & kTmaEpiDouble) ? 2 : 1;
+  // staging: nbuf (1..3) tiles per warp, used round-robin.  A tile may only be rewritten once the TMA store that last read
+  // it has finished reading; with a single tile that wait (TMA queue latency, ~1 us behind the producer's loads) sits
+  // on every tile's critical path - measured as the limiter of the 32->32@128x128 layers.  Without a residual, nbuf = 2
+  // lets one store stay in flight; with a residual the NEXT tile's residual is prefetched one tile ahead into the tile
+  // after the current one, so nbuf = 3 keeps both the prefetch and one store off the critical path.
+  const int nbuf = tc_epi_nbuf(tma_epi);
   uint8_t* stg0 = epi_smem + ew * nbuf * tc_epi_stage_bytes(NT);
-  uint64_t* rbar = &res_bar[ew * 2];
+  uint64_t* rbar = &res_bar[ew * 3];
   constexpr int ACC = AccCfg<1>::ACC;
   pdl_wait();                                 // residual reads / output writes must follow the predecessor grids
   auto load_res = [&](int tile, int buf) {    // lane 0 only
@@ -378,20 +388,26 @@ __device__ __forceinline__ void tc_epilogue_loop_tma(const ConvParams& p, const 
                 (rem / tiles_x) * 16 + q * 4, n);
   };
   const int first_tile = blockIdx.x + group * gridDim.x;
-  if (nbuf == 2 && has_res && lane == 0 && first_tile < num_tiles) load_res(first_tile, 0);
-  int it = group, t_local = 0;
+  if (nbuf >= 2 && has_res && lane == 0 && first_tile < num_tiles) load_res(first_tile, 0);
+  int it = group, t_local = 0, buf = 0;
+  uint32_t rphase = 0;
   for (int tile = first_tile; tile < num_tiles; tile += 2 * gridDim.x, it += 2, ++t_local) {
     const int acc = it & (ACC - 1);
     const int n = tile / per_frame, rem = tile % per_frame;
     const int y0 = (rem / tiles_x) * 16 + q * 4, x0 = (rem % tiles_x) * 8;     // this warp's 4 x 8 pixel box
-    const int buf = nbuf == 2 ? (t_local & 1) : 0;
     uint8_t* stg = stg0 + buf * tc_epi_stage_bytes(NT);
-    const uint32_t rphase = (uint32_t)(nbuf == 2 ? (t_local >> 1) : t_local) & 1u;
+    const int buf_next = buf + 1 == nbuf ? 0 : buf + 1;
     if (lane == 0) {
-      bulk_wait_read0();                      // the previous tile's store has finished reading its staging tile
       if (has_res) {
-        if (nbuf == 1) load_res(tile, 0);
-        else if (tile + 2 * (int)gridDim.x < num_tiles) load_res(tile + 2 * gridDim.x, buf ^ 1);
+        if (nbuf == 1) {
+          bulk_wait_read(0);
+          load_res(tile, 0);
+        } else {
+          bulk_wait_read(nbuf - 2);             // the store that last read staging tile buf_next is done
+          if (tile + 2 * (int)gridDim.x < num_tiles) load_res(tile + 2 * gridDim.x, buf_next);
+        }
+      } else {
+        bulk_wait_read(nbuf - 1);               // the store that last read staging tile buf is done
       }
     }
     __syncwarp();
@@ -449,6 +465,8 @@ __device__ __forceinline__ void tc_epilogue_loop_tma(const ConvParams& p, const 
       tma_store_4d(&maps.out, stg, p.out_c_off + co0, x0, y0, n);
       bulk_commit_group();
     }
+    if (buf_next == 0) rphase ^= 1;           // every staging tile (and its residual barrier) was used once more
+    buf = buf_next;
   }
   if (lane == 0) bulk_wait0();                // all stores performed before the CTA's shared memory goes away
   __syncwarp();
@@ -469,6 +487,17 @@ static inline cudaError_t tc_launch(void (*kern)(KArgs...), dim3 grid, int threa
   cfg.attrs = at;
   cfg.numAttrs = pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+// staging tiles per epilogue warp for a plan with `avail` bytes left for staging + pipeline stages: as many as useful
+// (3 with a residual, 2 without) while keeping >= 6 stages, else >= 4, else >= 2; 0 = the TMA epilogue does not fit
+inline int tc_epi_pick_nbuf(int tma_epi, int nt, int avail, int stage_bytes) {
+  const int maxb = (tma_epi & kTmaEpiRes) ? 3 : 2;
+  const int wants[3] = {6, 4, 2};
+  for (int w = 0; w < 3; ++w)
+    for (int nb = maxb; nb >= 1; --nb)
+      if ((avail - tc_epi_total_bytes(tc_epi_with_nbuf(tma_epi, nb), nt)) / stage_bytes >= wants[w]) return nb;
+  return 0;
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
