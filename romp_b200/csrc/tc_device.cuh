@@ -242,12 +242,13 @@ __device__ __forceinline__ void tc_store32(const ConvParams& p, size_t pix, size
   }
 }
 
-// TMEM accumulator organisation.  A tcgen05.mma that accumulates into the SAME TMEM tile as its predecessor cannot
-// overlap with it (measured: ~120 clk per dependent MMA whatever N is), so the K loop of one tile is spread
-// round-robin over KSPLIT independent accumulators that the epilogue adds up; ACC tiles are in flight.
+// TMEM accumulator ring: ACC tiles in flight per CTA (8 x NT <= 512 columns for NT <= 64).  The ring depth bounds the
+// throughput by (tiles in flight) / (MMA -> commit -> epilogue wake-up -> tcgen05.ld -> tmem_empty arrive -> MMA wake-up
+// round trip); with 4 stages the 32->32@128x128 pair kernel was measured waiting on exactly this loop (MMA thread spinning
+// on tmem_empty while the epilogue spun on tmem_full).  (KSPLIT > 1 = the abandoned K-split experiment, 2 tiles.)
 template <int KSPLIT>
 struct AccCfg {
-  static constexpr int ACC = KSPLIT == 1 ? 4 : 2;
+  static constexpr int ACC = KSPLIT == 1 ? 8 : 2;
 };
 // accumulators per tile: as many as TMEM allows (2 tiles x KSPLIT x NT <= 512 columns), never more than the MMAs of a tile
 __host__ __device__ constexpr int tc_ksplit(int mmas_per_tile, int nt) {
