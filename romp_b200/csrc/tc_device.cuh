@@ -390,12 +390,18 @@ __device__ __forceinline__ void tc_epilogue_loop_tma(const ConvParams& p, const 
   };
   const int first_tile = blockIdx.x + group * gridDim.x;
   if (nbuf >= 2 && has_res && lane == 0 && first_tile < num_tiles) load_res(first_tile, 0);
+  const bool relu = p.relu != 0;
+  const uint32_t bias_saddr = smem_u32(s_bias);
+  // (frame, tile-in-frame) advance incrementally: two integer divisions per tile were ~25 % of this loop's instructions
+  const int tstep = 2 * (int)gridDim.x, step_n = tstep / per_frame, step_rem = tstep % per_frame;
+  const int tx_shift = (tiles_x & (tiles_x - 1)) == 0 ? __ffs(tiles_x) - 1 : -1;
+  int n = first_tile / per_frame, rem = first_tile % per_frame;
   int it = group, t_local = 0, buf = 0;
   uint32_t rphase = 0;
-  for (int tile = first_tile; tile < num_tiles; tile += 2 * gridDim.x, it += 2, ++t_local) {
+  for (int tile = first_tile; tile < num_tiles; tile += tstep, it += 2, ++t_local) {
     const int acc = it & (ACC - 1);
-    const int n = tile / per_frame, rem = tile % per_frame;
-    const int y0 = (rem / tiles_x) * 16 + q * 4, x0 = (rem % tiles_x) * 8;     // this warp's 4 x 8 pixel box
+    const int ty = tx_shift >= 0 ? (rem >> tx_shift) : rem / tiles_x, tx = rem - ty * tiles_x;
+    const int y0 = ty * 16 + q * 4, x0 = tx * 8;                               // this warp's 4 x 8 pixel box
     uint8_t* stg = stg0 + buf * tc_epi_stage_bytes(NT);
     const int buf_next = buf + 1 == nbuf ? 0 : buf + 1;
     if (lane == 0) {
@@ -431,7 +437,14 @@ __device__ __forceinline__ void tc_epilogue_loop_tma(const ConvParams& p, const 
       }
       float v[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + s_bias[c0 + j];
+      for (int j4 = 0; j4 < 8; ++j4) {        // bias: 8 x ld.shared.v4 (the generic-pointer form compiled to slow generic loads)
+        float4 b;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(bias_saddr + (c0 + 4 * j4) * 4));
+        v[4 * j4 + 0] = __uint_as_float(r[4 * j4 + 0]) + b.x;
+        v[4 * j4 + 1] = __uint_as_float(r[4 * j4 + 1]) + b.y;
+        v[4 * j4 + 2] = __uint_as_float(r[4 * j4 + 2]) + b.z;
+        v[4 * j4 + 3] = __uint_as_float(r[4 * j4 + 3]) + b.w;
+      }
       if (has_res) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -444,10 +457,8 @@ __device__ __forceinline__ void tc_epilogue_loop_tma(const ConvParams& p, const 
           }
         }
       }
-      if (p.relu) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-      }
+      // round to bf16 first, ReLU on the packed pairs: max(round(x), 0) == round(max(x, 0)) (rounding is monotonic, 0 exact)
+      const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         uint4 pk;
@@ -455,6 +466,7 @@ __device__ __forceinline__ void tc_epilogue_loop_tma(const ConvParams& p, const 
         __nv_bfloat162 h1 = __floats2bfloat162_rn(v[i * 8 + 2], v[i * 8 + 3]);
         __nv_bfloat162 h2 = __floats2bfloat162_rn(v[i * 8 + 4], v[i * 8 + 5]);
         __nv_bfloat162 h3 = __floats2bfloat162_rn(v[i * 8 + 6], v[i * 8 + 7]);
+        if (relu) { h0 = __hmax2(h0, zero2); h1 = __hmax2(h1, zero2); h2 = __hmax2(h2, zero2); h3 = __hmax2(h3, zero2); }
         pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
         pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
         *tc_epi_chunk<NT>(stg, lane, c0 / 8 + i) = pk;
@@ -468,6 +480,8 @@ __device__ __forceinline__ void tc_epilogue_loop_tma(const ConvParams& p, const 
     }
     if (buf_next == 0) rphase ^= 1;           // every staging tile (and its residual barrier) was used once more
     buf = buf_next;
+    n += step_n; rem += step_rem;
+    if (rem >= per_frame) { rem -= per_frame; ++n; }
   }
   if (lane == 0) bulk_wait0();                // all stores performed before the CTA's shared memory goes away
   __syncwarp();
