@@ -54,7 +54,7 @@ conv_stem_tc_kernel(const __grid_constant__ CUtensorMap raw_map, const __grid_co
   uint64_t* res_bar = tmem_empty + kStemAcc;
   uint64_t* raw_full = res_bar + 3 * kEpiWarps;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(raw_full + kStemStages * kRawDepth);
-  float* s_bias = reinterpret_cast<float*>(tmem_ptr + 2);
+  float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr + 2) + 15) & ~(uintptr_t)15);   // 16 B: ld.shared.v4
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
