@@ -427,14 +427,7 @@ __device__ __forceinline__ void tc_epilogue_loop_tma(const ConvParams& p, const 
       uint32_t r[32];
       tmem_ld32(taddr + c0, r);
       tmem_ld_wait();
-      if (c0 + 32 == NT) {                    // accumulator fully read: hand the TMEM stage back before the stores
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (CTA2) mbar_arrive_cluster(&tmem_empty[acc], 0);   // the pair's leader issues the MMAs of both CTAs
-          else mbar_arrive(&tmem_empty[acc]);
-        }
-      }
+      if (c0 + 32 == NT) tc_fence_before();   // accumulator fully read (released below, after the store is issued)
       float v[32];
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4) {        // bias: 8 x ld.shared.v4 (the generic-pointer form compiled to slow generic loads)
@@ -477,6 +470,10 @@ __device__ __forceinline__ void tc_epilogue_loop_tma(const ConvParams& p, const 
     if (lane == 0) {
       tma_store_4d(&maps.out, stg, p.out_c_off + co0, x0, y0, n);
       bulk_commit_group();
+      // Hand the TMEM stage back.  Done after the proxy fence on purpose: fence.proxy.async compiles to MEMBAR.ALL.CTA,
+      // which would otherwise wait for this (for the pair's peer CTA: remote) arrive to be performed on every tile.
+      if (CTA2) mbar_arrive_cluster(&tmem_empty[acc], 0);     // the pair's leader issues the MMAs of both CTAs
+      else mbar_arrive(&tmem_empty[acc]);
     }
     if (buf_next == 0) rphase ^= 1;           // every staging tile (and its residual barrier) was used once more
     buf = buf_next;
