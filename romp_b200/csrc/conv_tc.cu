@@ -172,6 +172,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         umma_commit(&tmem_full[acc]);            // accumulator complete -> epilogue
       }
     }
+  } else if (KSPLIT == 1 && (tma_epi & kEpiCoalesced)) {
+    tc_epilogue_loop_coalesced<NT>(p, tma_epi, epi_smem, tmem_base, tmem_full, tmem_empty, s_bias, tiles_x, per_frame, num_tiles);
   } else if (KSPLIT == 1 && tma_epi) {
     tc_epilogue_loop_tma<NT>(p, epi_maps, tma_epi, epi_smem, res_bar, tmem_base, tmem_full, tmem_empty, s_bias, tiles_x, per_frame,
                              num_tiles);
@@ -354,7 +356,7 @@ int tc_conv_prepare(const ConvParams& p, int ksize, int stride, const float* w_o
     const int nb = tc_epi_pick_nbuf(plan->tma_epi, nt, budget - bbytes(nt), stage_bytes);
     if (nb == 0) plan->tma_epi = 0;
     else {
-      plan->tma_epi = tc_epi_with_nbuf(plan->tma_epi, nb);
+      plan->tma_epi = tc_epi_with_nbuf(plan->tma_epi, nb) | (tc_epi_want_coalesced(nt) ? kEpiCoalesced : 0);
       epi_bytes = tc_epi_total_bytes(plan->tma_epi, nt);
     }
   }

@@ -160,8 +160,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       }
     }
   } else {
-    tc_epilogue_loop_tma<NT, true>(p, epi_maps, tma_epi, epi_smem, res_bar, tmem_base, tmem_full, tmem_empty, s_bias, tiles_x,
-                                   per_frame, num_tiles);
+    if (tma_epi & kEpiCoalesced)
+      tc_epilogue_loop_coalesced<NT, true>(p, tma_epi, epi_smem, tmem_base, tmem_full, tmem_empty, s_bias, tiles_x, per_frame, num_tiles);
+    else
+      tc_epilogue_loop_tma<NT, true>(p, epi_maps, tma_epi, epi_smem, res_bar, tmem_base, tmem_full, tmem_empty, s_bias, tiles_x,
+                                     per_frame, num_tiles);
   }
   tc_fence_before();
   cluster_sync_all();                               // no CTA leaves while its peer may still address its barriers / TMEM
@@ -259,7 +262,7 @@ int tc2_try_prepare(const ConvParams& p, int ksize, int stride, const float* w_o
   if (!tc_epi_prepare(p, nt, ptrs_final, plan)) return 0;               // the pair engine only has the TMA epilogue
   const int nb = tc_epi_pick_nbuf(plan->tma_epi, nt, budget - bbytes(nt), stage_bytes);
   if (nb == 0) return 0;
-  plan->tma_epi = tc_epi_with_nbuf(plan->tma_epi, nb);
+  plan->tma_epi = tc_epi_with_nbuf(plan->tma_epi, nb) | (tc_epi_want_coalesced(nt) ? kEpiCoalesced : 0);
   const int epi_bytes = tc_epi_total_bytes(plan->tma_epi, nt);
   int stages = std::min(8, (budget - bbytes(nt) - epi_bytes) / stage_bytes);
   plan->kind = 34;

@@ -160,6 +160,8 @@ conv_tc_s2_kernel(const __grid_constant__ S2Maps maps, const __grid_constant__ T
         umma_commit(&tmem_full[acc]);
       }
     }
+  } else if (KSPLIT == 1 && (tma_epi & kEpiCoalesced)) {
+    tc_epilogue_loop_coalesced<NT>(p, tma_epi, epi_smem, tmem_base, tmem_full, tmem_empty, s_bias, tiles_x, per_frame, num_tiles);
   } else if (KSPLIT == 1 && tma_epi) {
     tc_epilogue_loop_tma<NT>(p, epi_maps, tma_epi, epi_smem, res_bar, tmem_base, tmem_full, tmem_empty, s_bias, tiles_x, per_frame,
                              num_tiles);
@@ -241,6 +243,7 @@ int tc_s2_prepare(const ConvParams& p, const float* w_oihw, int sm_count, bool p
   // TMA epilogue only where it does not cost the second pipeline stage
   int epi_bytes = 0;
   if (tc_epi_prepare(p, nt, ptrs_final, plan)) {
+    if (tc_epi_want_coalesced(nt)) plan->tma_epi |= kEpiCoalesced;
     epi_bytes = tc_epi_total_bytes(plan->tma_epi, nt);
     const int without = (budget - bbytes(nt)) / stage_bytes, with = (budget - bbytes(nt) - epi_bytes) / stage_bytes;
     if (with < 1 || (with < 2 && without >= 2)) { plan->tma_epi = 0; epi_bytes = 0; }

@@ -371,7 +371,8 @@ __device__ __forceinline__ void tc_epilogue_loop_tma(const ConvParams& p, const 
   const int group = ew >> 2;
   const int q = warp & 3;
   const int co0 = blockIdx.y * NT;
-  const bool has_res = (tma_epi & kTmaEpiRes) != 0;
+  const bool dbg_quiet = (p.debug & 1) != 0;   // B200ROMP_TC_DEBUG bit 0: epilogue without global traffic (profiling experiments)
+  const bool has_res = (tma_epi & kTmaEpiRes) != 0 && !dbg_quiet;
   // staging: nbuf (1..3) tiles per warp, used round-robin.  A tile may only be rewritten once the TMA store that last read
   // it has finished reading; with a single tile that wait (TMA queue latency, ~1 us behind the producer's loads) sits
   // on every tile's critical path - measured as the limiter of the 32->32@128x128 layers.  Without a residual, nbuf = 2
@@ -468,8 +469,10 @@ __device__ __forceinline__ void tc_epilogue_loop_tma(const ConvParams& p, const 
     fence_proxy_async();                      // generic-proxy writes -> visible to the TMA store
     __syncwarp();
     if (lane == 0) {
-      tma_store_4d(&maps.out, stg, p.out_c_off + co0, x0, y0, n);
-      bulk_commit_group();
+      if (!dbg_quiet) {
+        tma_store_4d(&maps.out, stg, p.out_c_off + co0, x0, y0, n);
+        bulk_commit_group();
+      }
       // Hand the TMEM stage back.  Done after the proxy fence on purpose: fence.proxy.async compiles to MEMBAR.ALL.CTA,
       // which would otherwise wait for this (for the pair's peer CTA: remote) arrive to be performed on every tile.
       if (CTA2) mbar_arrive_cluster(&tmem_empty[acc], 0);     // the pair's leader issues the MMAs of both CTAs
@@ -501,10 +504,149 @@ static inline cudaError_t tc_launch(void (*kern)(KArgs...), dim3 grid, int threa
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
+// ---- coalesced direct epilogue ----------------------------------------------------------------------
+// Same in-place staging tile as the TMA epilogue, but the global traffic is done by the warp itself: the staging tile is
+// read back "transposed" (NT/8 consecutive lanes = the NT channels of one pixel, so one warp-wide 16 B access covers
+// 512 contiguous bytes when the tensor has NT channels) and written with plain st.global.v4; the residual comes in by
+// the mirror-image ld.global.v4, software-pipelined one tile ahead in registers.  Why: the TMA unit retires roughly one
+// box ROW per 2 clk whatever its length (measured: 32->32@128x128, 64 B rows: 45 us with the TMA epilogue, 26 us with the
+// epilogue's global traffic disabled, and the same ratio on 128 B rows costs only 2 us) - with 64 B rows the store and
+// residual boxes (256 rows per tile) overload it next to the 180 rows of the halo load.
+constexpr int kEpiCoalesced = 16;   // bit in plan->tma_epi: use tc_epilogue_loop_coalesced instead of the TMA epilogue
+template <int NT, bool CTA2 = false>
+__device__ __forceinline__ void tc_epilogue_loop_coalesced(const ConvParams& p, int tma_epi, uint8_t* epi_smem, uint32_t tmem_base,
+                                                           uint64_t* tmem_full, uint64_t* tmem_empty, const float* s_bias,
+                                                           int tiles_x, int per_frame, int num_tiles) {
+  static_assert(NT == 32 || NT == 64, "staging layout");
+  constexpr int CH = NT / 8;                  // 16 B chunks per pixel = lanes per pixel in the transposed pattern
+  constexpr int PPI = 32 / CH;                // pixels per warp-wide access
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ew = warp - kFirstEpiWarp;
+  const int group = ew >> 2;
+  const int q = warp & 3;
+  const int co0 = blockIdx.y * NT;
+  const bool dbg_quiet = (p.debug & 1) != 0;
+  const bool has_res = p.res != nullptr && !dbg_quiet;
+  const bool relu = p.relu != 0;
+  uint8_t* stg = epi_smem + ew * tc_epi_nbuf(tma_epi) * tc_epi_stage_bytes(NT);
+  const uint32_t bias_saddr = smem_u32(s_bias);
+  constexpr int ACC = AccCfg<1>::ACC;
+  const int tp = lane / CH, tc = lane % CH;   // transposed role of this lane: pixel-in-group, chunk
+  pdl_wait();
+  const int tstep = 2 * (int)gridDim.x, step_n = tstep / per_frame, step_rem = tstep % per_frame;
+  const int tx_shift = (tiles_x & (tiles_x - 1)) == 0 ? __ffs(tiles_x) - 1 : -1;
+  const int first_tile = blockIdx.x + group * gridDim.x;
+  int n = first_tile / per_frame, rem = first_tile % per_frame;
+  // element offset (in 16 B units) of transposed access i of the tile whose box starts at (n, y0, x0)
+  auto goff = [&](const int C_total, const int c_off, int nn, int y0, int x0, int i) -> size_t {
+    const int pp = i * PPI + tp;              // pixel 0..31 of the warp's 4 x 8 box
+    const size_t pix = ((size_t)nn * p.Hout + y0 + (pp >> 3)) * p.Wout + x0 + (pp & 7);
+    return (pix * C_total + c_off + co0) / 8 + tc;
+  };
+  auto box_of = [&](int r, int& y0, int& x0) {
+    const int ty = tx_shift >= 0 ? (r >> tx_shift) : r / tiles_x, tx = r - ty * tiles_x;
+    y0 = ty * 16 + q * 4; x0 = tx * 8;
+  };
+  const uint4* res16 = reinterpret_cast<const uint4*>(p.res);
+  uint4* out16 = reinterpret_cast<uint4*>(p.out);
+  uint4 rnext[CH];
+  if (has_res && first_tile < num_tiles) {
+    int y0, x0;
+    box_of(rem, y0, x0);
+#pragma unroll
+    for (int i = 0; i < CH; ++i) rnext[i] = res16[goff(p.res_C, p.res_c_off, n, y0, x0, i)];
+  }
+  int it = group;
+  for (int tile = first_tile; tile < num_tiles; tile += tstep, it += 2) {
+    const int acc = it & (ACC - 1);
+    int y0, x0;
+    box_of(rem, y0, x0);
+    int n2 = n + step_n, rem2 = rem + step_rem;
+    if (rem2 >= per_frame) { rem2 -= per_frame; ++n2; }
+    if (has_res) {
+      // this tile's residual (fetched during the previous tile) -> staging; then prefetch the next tile's
+#pragma unroll
+      for (int i = 0; i < CH; ++i) *tc_epi_chunk<NT>(stg, i * PPI + tp, tc) = rnext[i];
+      if (tile + tstep < num_tiles) {
+        int y1, x1;
+        box_of(rem2, y1, x1);
+#pragma unroll
+        for (int i = 0; i < CH; ++i) rnext[i] = res16[goff(p.res_C, p.res_c_off, n2, y1, x1, i)];
+      }
+      __syncwarp();
+    }
+    mbar_wait(&tmem_full[acc], (it / ACC) & 1);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT);
+#pragma unroll
+    for (int c0 = 0; c0 < NT; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(taddr + c0, r);
+      tmem_ld_wait();
+      if (c0 + 32 == NT) {                    // accumulator fully read: hand the TMEM stage back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CTA2) mbar_arrive_cluster(&tmem_empty[acc], 0);
+          else mbar_arrive(&tmem_empty[acc]);
+        }
+      }
+      float v[32];
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        float4 b;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(bias_saddr + (c0 + 4 * j4) * 4));
+        v[4 * j4 + 0] = __uint_as_float(r[4 * j4 + 0]) + b.x;
+        v[4 * j4 + 1] = __uint_as_float(r[4 * j4 + 1]) + b.y;
+        v[4 * j4 + 2] = __uint_as_float(r[4 * j4 + 2]) + b.z;
+        v[4 * j4 + 3] = __uint_as_float(r[4 * j4 + 3]) + b.w;
+      }
+      if (has_res) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint4 t = *tc_epi_chunk<NT>(stg, lane, c0 / 8 + i);
+          const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            v[i * 8 + 2 * k] += __uint_as_float(w[k] << 16);
+            v[i * 8 + 2 * k + 1] += __uint_as_float(w[k] & 0xffff0000u);
+          }
+        }
+      }
+      const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 pk;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[i * 8 + 0], v[i * 8 + 1]);
+        __nv_bfloat162 h1 = __floats2bfloat162_rn(v[i * 8 + 2], v[i * 8 + 3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[i * 8 + 4], v[i * 8 + 5]);
+        __nv_bfloat162 h3 = __floats2bfloat162_rn(v[i * 8 + 6], v[i * 8 + 7]);
+        if (relu) { h0 = __hmax2(h0, zero2); h1 = __hmax2(h1, zero2); h2 = __hmax2(h2, zero2); h3 = __hmax2(h3, zero2); }
+        pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+        pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+        *tc_epi_chunk<NT>(stg, lane, c0 / 8 + i) = pk;
+      }
+    }
+    __syncwarp();
+    if (!dbg_quiet) {
+#pragma unroll
+      for (int i = 0; i < CH; ++i) out16[goff(p.out_C, p.out_c_off, n, y0, x0, i)] = *tc_epi_chunk<NT>(stg, i * PPI + tp, tc);
+    }
+    __syncwarp();                             // staging tile is rewritten by the next tile's residual / outputs
+    n = n2; rem = rem2;
+  }
+}
+
 // staging tiles per epilogue warp for a plan with `avail` bytes left for staging + pipeline stages: as many as useful
 // (3 with a residual, 2 without) while keeping >= 6 stages, else >= 4, else >= 2; 0 = the TMA epilogue does not fit
+// policy: 64-byte box rows (NT = 32) overload the TMA unit -> coalesced direct epilogue; B200ROMP_EPI_COALESCED=0|1 forces it
+inline bool tc_epi_want_coalesced(int nt) {
+  static const int mode = [] { const char* e = getenv("B200ROMP_EPI_COALESCED"); return e ? atoi(e) : -1; }();
+  return mode < 0 ? nt == 32 : mode != 0;
+}
 inline int tc_epi_pick_nbuf(int tma_epi, int nt, int avail, int stage_bytes) {
-  const int maxb = (tma_epi & kTmaEpiRes) ? 3 : 2;
+  if (tc_epi_want_coalesced(nt)) return (avail - tc_epi_total_bytes(tc_epi_with_nbuf(tma_epi, 1), nt)) / stage_bytes >= 2 ? 1 : 0;
+  const int maxb = 3;
   const int wants[3] = {6, 4, 2};
   for (int w = 0; w < 3; ++w)
     for (int nb = maxb; nb >= 1; --nb)
