@@ -89,6 +89,7 @@ conv_stem_tc_kernel(const __grid_constant__ CUtensorMap raw_map, const __grid_co
       bulk_copy_g2s(sB, wpack, kStemBBytes, b_full);
     }
     pdl_wait();                                  // frames may be produced by a predecessor kernel / copy
+    const uint64_t pol = l2_policy_stream(p.debug);
     uint8_t* a = sA + pw * kStemABytes;
     uint8_t* raw0 = raw_smem + pw * kRawDepth * kStemRawStride;
     uint64_t* rbar = raw_full + pw * kRawDepth;
@@ -96,7 +97,7 @@ conv_stem_tc_kernel(const __grid_constant__ CUtensorMap raw_map, const __grid_co
       const int n = tile / per_frame, rem = tile % per_frame;
       const int y0 = (rem / tiles_x) * 16, x0 = (rem % tiles_x) * 8;
       mbar_arrive_expect_tx(&rbar[slot], kRawBytes);
-      tma_load_3d(raw0 + slot * kStemRawStride, &raw_map, &rbar[slot], 6 * x0 - 16, 2 * y0 - 1, n);
+      tma_load_3d(raw0 + slot * kStemRawStride, &raw_map, &rbar[slot], 6 * x0 - 16, 2 * y0 - 1, n, pol);
     };
     const int tstep = kStemStages * gridDim.x;
     const int first = blockIdx.x + pw * gridDim.x;

@@ -102,6 +102,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       for (int i = 0; i < Cfg::TAPS * Cfg::KCH; ++i)
         bulk_copy_g2s(sB + (size_t)i * Cfg::BTILE, wsrc + (size_t)i * Cfg::BTILE, Cfg::BTILE, b_full);
       pdl_wait();                             // weights are constants; activations must wait for the predecessor grids
+      const uint64_t pol = l2_policy_stream(p.debug);
       // Each MMA warp owns a private stage ring (ring r = stages [ring_base(r), ring_base(r) + ring_size(r))): mbarrier
       // waits only see the phase parity, so a ring must have exactly one in-order consumer (TMA completions of
       // different stages arrive out of order, a shared ring would alias phases).  Tile i of this CTA goes to ring i & 1.
@@ -122,7 +123,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
               mbar_arrive_expect_tx(&full[sidx], Cfg::STAGE_PAYLOAD);
               const int dy = PER_TAP ? l / KS - Cfg::PAD : -Cfg::PAD;
               const int dx = PER_TAP ? l % KS - Cfg::PAD : -Cfg::PAD;
-              tma_load_4d(sA + (size_t)sidx * Cfg::STAGE_BYTES, &tmap, &full[sidx], c * Cfg::CW, x0 + dx, y0 + dy, n);
+              tma_load_4d(sA + (size_t)sidx * Cfg::STAGE_BYTES, &tmap, &full[sidx], c * Cfg::CW, x0 + dx, y0 + dy, n, pol);
             }
             if (++stage == rsize) { stage = 0; phase ^= 1; }
           }

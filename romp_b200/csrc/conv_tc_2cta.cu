@@ -95,6 +95,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       for (int i = 0; i < Cfg::TAPS * Cfg::KCH; ++i)
         bulk_copy_g2s(sB + (size_t)i * Cfg::BTILE, wsrc + (size_t)i * Cfg::BTILE, Cfg::BTILE, b_full);
       pdl_wait();
+      const uint64_t pol = l2_policy_stream(p.debug);
       int stage = 0, stage_other = 0;
       uint32_t phase = 0, phase_other = 0;
       int it = 0;
@@ -106,7 +107,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
           const int sidx = rbase + stage;
           mbar_wait(&empty[sidx], phase ^ 1);
           if (rank == 0) mbar_arrive_expect_tx(&full[sidx], 2 * Cfg::STAGE_PAYLOAD);      // own tile + the peer's
-          tma_load_4d_2cta(sA + (size_t)sidx * Cfg::STAGE_BYTES, &tmap, &full[sidx], c * Cfg::CW, x0 - 1, y0 - 1, n);
+          tma_load_4d_2cta(sA + (size_t)sidx * Cfg::STAGE_BYTES, &tmap, &full[sidx], c * Cfg::CW, x0 - 1, y0 - 1, n, pol);
           if (++stage == rsize) { stage = 0; phase ^= 1; }
         }
         if (nrings == 2) { const int ts = stage; stage = stage_other; stage_other = ts; const uint32_t tp = phase; phase = phase_other; phase_other = tp; }

@@ -14,10 +14,10 @@
 namespace b200romp {
 
 __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3,
-                                            int c4) {
+                                            int c4, uint64_t pol) {
   asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(pol)
       : "memory");
 }
 
@@ -97,6 +97,7 @@ conv_tc_s2_kernel(const __grid_constant__ S2Maps maps, const __grid_constant__ T
       for (int i = 0; i < 9 * Cfg::KCH; ++i)
         bulk_copy_g2s(sB + (size_t)i * Cfg::BTILE, wsrc + (size_t)i * Cfg::BTILE, Cfg::BTILE, b_full);
       pdl_wait();                             // weights are constants; activations must wait for the predecessor grids
+      const uint64_t pol = l2_policy_stream(p.debug);
       int stage = 0, stage_other = 0;                  // one private stage ring per MMA warp (see conv_tc.cu)
       uint32_t phase = 0, phase_other = 0;   // (stage, phase) of the current tile's ring / of the other ring
       int it = 0;
@@ -112,7 +113,7 @@ conv_tc_s2_kernel(const __grid_constant__ S2Maps maps, const __grid_constant__ T
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int ph = i < 2 ? 1 : 0, pw = (i & 1) ? 0 : 1;
-            tma_load_5d(dst + Cfg::SUB_OFF(i), &maps.m[i], &full[sidx], pw * CIN + c * Cfg::CW, x0 - pw, ph, y0 - ph, n);
+            tma_load_5d(dst + Cfg::SUB_OFF(i), &maps.m[i], &full[sidx], pw * CIN + c * Cfg::CW, x0 - pw, ph, y0 - ph, n, pol);
           }
           if (++stage == rsize) { stage = 0; phase ^= 1; }
         }

@@ -60,16 +60,26 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+// L2 eviction policy of activation loads.  Every activation tensor is read once (twice when it is also a residual) and the
+// batch-64 tensors are 33-537 MB against 126 MB of L2: with the default policy a layer's input stream evicts the output
+// it is producing, so the NEXT layer finds nothing in L2.  Loads tagged evict_first leave L2 first; the freshly written
+// outputs (default priority) survive and the next layer's main input hits L2.  B200ROMP_TC_DEBUG bit 3 disables the hint.
+__device__ __forceinline__ uint64_t l2_policy_stream(int debug) {
+  uint64_t pol;
+  if (debug & 8) asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, uint64_t pol) {
   asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, uint64_t pol) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(pol)
       : "memory");
 }
 // tensor store shared -> global (bulk async-group completion)
@@ -148,10 +158,10 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {   // arrives o
                ::"r"(smem_u32(bar)), "h"(mask)
                : "memory");
 }
-__device__ __forceinline__ void tma_load_4d_2cta(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+__device__ __forceinline__ void tma_load_4d_2cta(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, uint64_t pol) {
   asm volatile(
-      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -383,11 +393,12 @@ __device__ __forceinline__ void tc_epilogue_loop_tma(const ConvParams& p, const 
   uint64_t* rbar = &res_bar[ew * 3];
   constexpr int ACC = AccCfg<1>::ACC;
   pdl_wait();                                 // residual reads / output writes must follow the predecessor grids
+  const uint64_t res_pol = l2_policy_stream(p.debug);
   auto load_res = [&](int tile, int buf) {    // lane 0 only
     const int n = tile / per_frame, rem = tile % per_frame;
     mbar_arrive_expect_tx(&rbar[buf], tc_epi_stage_bytes(NT));
     tma_load_4d(stg0 + buf * tc_epi_stage_bytes(NT), &maps.res, &rbar[buf], p.res_c_off + co0, (rem % tiles_x) * 8,
-                (rem / tiles_x) * 16 + q * 4, n);
+                (rem / tiles_x) * 16 + q * 4, n, res_pol);
   };
   const int first_tile = blockIdx.x + group * gridDim.x;
   if (nbuf >= 2 && has_res && lane == 0 && first_tile < num_tiles) load_res(first_tile, 0);
@@ -639,10 +650,11 @@ __device__ __forceinline__ void tc_epilogue_loop_coalesced(const ConvParams& p, 
 
 // staging tiles per epilogue warp for a plan with `avail` bytes left for staging + pipeline stages: as many as useful
 // (3 with a residual, 2 without) while keeping >= 6 stages, else >= 4, else >= 2; 0 = the TMA epilogue does not fit
-// policy: 64-byte box rows (NT = 32) overload the TMA unit -> coalesced direct epilogue; B200ROMP_EPI_COALESCED=0|1 forces it
+// B200ROMP_EPI_COALESCED=1 selects the coalesced direct epilogue instead of the TMA epilogue
 inline bool tc_epi_want_coalesced(int nt) {
   static const int mode = [] { const char* e = getenv("B200ROMP_EPI_COALESCED"); return e ? atoi(e) : -1; }();
-  return mode < 0 ? nt == 32 : mode != 0;
+  (void)nt;
+  return mode > 0;   // measured equal to (NT = 32) or slower than the TMA epilogue: kept as an experiment switch
 }
 inline int tc_epi_pick_nbuf(int tma_epi, int nt, int avail, int stage_bytes) {
   if (tc_epi_want_coalesced(nt)) return (avail - tc_epi_total_bytes(tc_epi_with_nbuf(tma_epi, 1), nt)) / stage_bytes >= 2 ? 1 : 0;
