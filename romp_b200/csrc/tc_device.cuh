@@ -60,14 +60,15 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// L2 eviction policy of activation loads.  Every activation tensor is read once (twice when it is also a residual) and the
-// batch-64 tensors are 33-537 MB against 126 MB of L2: with the default policy a layer's input stream evicts the output
-// it is producing, so the NEXT layer finds nothing in L2.  Loads tagged evict_first leave L2 first; the freshly written
-// outputs (default priority) survive and the next layer's main input hits L2.  B200ROMP_TC_DEBUG bit 3 disables the hint.
+// L2 eviction policy of activation loads (experiment switch).  Idea: the batch-64 tensors are 33-537 MB against 126 MB of
+// L2, so a layer's input stream evicts the output it is producing; loads tagged evict_first should leave L2 first and let
+// the fresh outputs survive for the next layer.  Measured (per-op profile, B=64): 32->32@128x128 +res 47.3 -> 45.3 us, but
+// 1x1 64->256 +res 209 -> 256 us and 64->64@64x64 +res 25.4 -> 27.0 us - net slightly negative, so the default stays
+// evict_normal; B200ROMP_TC_DEBUG bit 3 (value 8) turns the evict_first hint on.
 __device__ __forceinline__ uint64_t l2_policy_stream(int debug) {
   uint64_t pol;
-  if (debug & 8) asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
-  else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  if (debug & 8) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, uint64_t pol) {
@@ -519,10 +520,10 @@ static inline cudaError_t tc_launch(void (*kern)(KArgs...), dim3 grid, int threa
 // Same in-place staging tile as the TMA epilogue, but the global traffic is done by the warp itself: the staging tile is
 // read back "transposed" (NT/8 consecutive lanes = the NT channels of one pixel, so one warp-wide 16 B access covers
 // 512 contiguous bytes when the tensor has NT channels) and written with plain st.global.v4; the residual comes in by
-// the mirror-image ld.global.v4, software-pipelined one tile ahead in registers.  Why: the TMA unit retires roughly one
-// box ROW per 2 clk whatever its length (measured: 32->32@128x128, 64 B rows: 45 us with the TMA epilogue, 26 us with the
-// epilogue's global traffic disabled, and the same ratio on 128 B rows costs only 2 us) - with 64 B rows the store and
-// residual boxes (256 rows per tile) overload it next to the 180 rows of the halo load.
+// the mirror-image ld.global.v4, software-pipelined one tile ahead in registers.  Written to test whether the TMA unit's
+// per-row cost (64 B box rows for NT = 32) is what makes the 32->32@128x128 layers slow: it is not - this path measures
+// 46.5 us against 41.0 / 46.9 us (without / with residual) for the TMA epilogue - so it stays an experiment switch
+// (B200ROMP_EPI_COALESCED=1); parity-tested like the default path.
 constexpr int kEpiCoalesced = 16;   // bit in plan->tma_epi: use tc_epilogue_loop_coalesced instead of the TMA epilogue
 template <int NT, bool CTA2 = false>
 __device__ __forceinline__ void tc_epilogue_loop_coalesced(const ConvParams& p, int tma_epi, uint8_t* epi_smem, uint32_t tmem_base,
