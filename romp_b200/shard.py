@@ -96,6 +96,80 @@ def all_gather_outputs(out, frame_offset: int, world: int, to_numpy: bool = True
     return {k: v.numpy() for k, v in unpack(fh[:ntot], ih[:ntot], layout).items()}
 
 
+class GatherPipeline:
+    """Pipelined all_gather_outputs for a stream of steps (the multi-GPU `forward_batches` loop).
+
+    submit() enqueues pack + the padded NCCL all-gathers + the device->host copies of the gathered rows on a side stream
+    and returns at once (only the tiny person-count exchange is synchronous); result() of the PREVIOUS step is collected
+    while the current step computes.  Host mirrors are double-buffered, so a result stays valid until the submit after
+    the next.  `host_rank`: rank that wants numpy results (None = every rank); other ranks only take part in the
+    collective and get None from result().  On a non-CUDA backend (gloo tests) everything runs synchronously.
+    """
+
+    def __init__(self, world: int, group=None, host_rank=None):
+        self.world, self.group, self.host_rank = world, group, host_rank
+        self.cuda = dist.get_backend(group) == "nccl"
+        self.stream = torch.cuda.Stream() if self.cuda else None
+        self.slot = 0
+
+    def submit(self, out, frame_offset: int):
+        if not self.cuda:
+            return ("done", all_gather_outputs(out, frame_offset, self.world, True, self.group))
+        rank = dist.get_rank(self.group)
+        want_host = self.host_rank is None or rank == self.host_rank
+        device = torch.device("cuda", torch.cuda.current_device())
+        frec, irec, layout = pack(out, frame_offset, device)
+        n = torch.tensor([frec.shape[0], frec.shape[1]], dtype=torch.int64, device=device)
+        counts = torch.zeros(self.world * 2, dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(counts, n, group=self.group)
+        counts = counts.cpu().view(self.world, 2)                  # the one synchronisation point (16 B per rank)
+        nmax, width = int(counts[:, 0].max()), int(counts[:, 1].max())
+        if nmax == 0:
+            return ("done", None)
+        if layout is None or width != DEFAULT_WIDTH:
+            # unusual key set: fall back to the synchronous path (agrees on the layout explicitly)
+            return ("done", all_gather_outputs(out, frame_offset, self.world, True, self.group))
+        ready = torch.cuda.Event()
+        ready.record()
+        slot, self.slot = self.slot, self.slot ^ 1
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            fpad = torch.zeros(nmax, width, device=device)
+            ipad = torch.zeros(nmax, 3, dtype=torch.int64, device=device)
+            if frec.shape[0]:
+                fpad[:frec.shape[0]] = frec
+                ipad[:irec.shape[0]] = irec
+            fall = torch.empty(self.world * nmax, width, device=device)
+            iall = torch.empty(self.world * nmax, 3, dtype=torch.int64, device=device)
+            dist.all_gather_into_tensor(fall, fpad, group=self.group)
+            dist.all_gather_into_tensor(iall, ipad, group=self.group)
+            ntot = int(counts[:, 0].sum())
+            fh = ih = None
+            if want_host:
+                fh, ih = _pinned(("f", slot), ntot, width, torch.float32), _pinned(("i", slot), ntot, 3, torch.int64)
+                row = 0
+                for r in range(self.world):
+                    c = int(counts[r, 0])
+                    if c:
+                        fh[row:row + c].copy_(fall[r * nmax:r * nmax + c], non_blocking=True)
+                        ih[row:row + c].copy_(iall[r * nmax:r * nmax + c], non_blocking=True)
+                        row += c
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        for t in (frec, irec, fpad, ipad, fall, iall):
+            t.record_stream(self.stream)
+        return ("pending", done, fh, ih, ntot, (fall, iall))
+
+    def result(self, handle):
+        if handle[0] == "done":
+            return handle[1]
+        _, done, fh, ih, ntot, _keep = handle
+        done.synchronize()
+        if fh is None:
+            return None
+        return {k: v.numpy() for k, v in unpack(fh[:ntot], ih[:ntot], DEFAULT_LAYOUT).items()}
+
+
 DEFAULT_LAYOUT = [("cam", (3,)), ("smpl_thetas", (72,)), ("smpl_betas", (10,)), ("center_confs", (1,)), ("cam_trans", (3,)),
                   ("joints", (71, 3)), ("pj2d_org", (71, 2)), ("verts", (6890, 3))]
 DEFAULT_WIDTH = sum(int(np.prod(s)) for _, s in DEFAULT_LAYOUT)

@@ -41,6 +41,11 @@ def worker(rank, world, port, total, q):
     lo, hi = shard.shard_range(total, rank, world)
     out = fake_outputs(list(range(lo, hi)), rank)
     res = shard.all_gather_outputs(out, lo, world)
+    pipe = shard.GatherPipeline(world)                 # the pipelined form must give the same answer (sync on gloo)
+    res2 = pipe.result(pipe.submit(out, lo))
+    assert (res is None) == (res2 is None)
+    if res is not None:
+        assert all(np.array_equal(res[k], res2[k]) for k in res)
     q.put((rank, None if res is None else {k: v for k, v in res.items()}))
     dist.destroy_process_group()
 
