@@ -161,7 +161,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       }
     }
   } else {
-    if (tma_epi & kEpiCoalesced)
+    if (NT == 32 && (tma_epi & kEpiCoalesced))
       tc_epilogue_loop_coalesced<NT, true>(p, tma_epi, epi_smem, tmem_base, tmem_full, tmem_empty, s_bias, tiles_x, per_frame, num_tiles);
     else
       tc_epilogue_loop_tma<NT, true>(p, epi_maps, tma_epi, epi_smem, res_bar, tmem_base, tmem_full, tmem_empty, s_bias, tiles_x,

@@ -654,8 +654,7 @@ __device__ __forceinline__ void tc_epilogue_loop_coalesced(const ConvParams& p, 
 // B200ROMP_EPI_COALESCED=1 selects the coalesced direct epilogue instead of the TMA epilogue
 inline bool tc_epi_want_coalesced(int nt) {
   static const int mode = [] { const char* e = getenv("B200ROMP_EPI_COALESCED"); return e ? atoi(e) : -1; }();
-  (void)nt;
-  return mode > 0;   // measured equal to (NT = 32) or slower than the TMA epilogue: kept as an experiment switch
+  return mode > 0 && nt == 32;   // measured equal to (NT = 32) or slower than the TMA epilogue: kept as an experiment switch
 }
 inline int tc_epi_pick_nbuf(int tma_epi, int nt, int avail, int stage_bytes) {
   if (tc_epi_want_coalesced(nt)) return (avail - tc_epi_total_bytes(tc_epi_with_nbuf(tma_epi, 1), nt)) / stage_bytes >= 2 ? 1 : 0;
