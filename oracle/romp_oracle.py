@@ -127,7 +127,7 @@ def coord_maps(size=128):
 
 def romp_head(sd, feat):
     """ROMPv1.forward after the backbone, model.py:470-481 (+ head layout :445-468)."""
-    x = torch.cat([feat, coord_maps(128).expand(feat.shape[0], -1, -1, -1)], 1)
+    x = torch.cat([feat, coord_maps(128).to(feat.device).expand(feat.shape[0], -1, -1, -1)], 1)
     outs = {}
     for h in (1, 2, 3):
         q = f"final_layers.{h}."
