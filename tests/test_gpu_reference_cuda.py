@@ -13,7 +13,9 @@ import torch
 from oracle import romp_oracle as O
 from romp_b200 import synth
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("B200ROMP_RUN_COMPARATOR") != "1",
+                                 reason="comparator timing takes ~4 min of cuDNN autotuning; set B200ROMP_RUN_COMPARATOR=1")]
 
 
 def _time(fn, iters=3):
