@@ -14,12 +14,17 @@
 //            descriptors* into that same halo tile: start address + (r*10+s) pixel rows, stride-byte-offset
 //            = 10 pixel rows (one image row of the halo), so the input is read from L2 once, not 9 times.
 //            Zero padding comes from TMA out-of-bounds fill (negative start coordinates).
-//   D: fp32 accumulators in TMEM, ring of 4 (4 x NT columns) so epilogues overlap the MMAs of later tiles.
-//   Epilogue (2 groups x 4 warps, one TMEM lane quarter per warp, groups alternate tiles): tcgen05.ld 32x32b.x32
-//            -> +bias (smem) -> residual / ReLU / nearest-upsample replication / dtype conversion with batched
-//            16-byte global accesses.
-// Warp roles: warp0 = TMA producer, warp1 = TMEM allocator + single-thread MMA issuer, warps2-9 = epilogue.
-// Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), persistent tile loop.
+//   D: fp32 accumulators in TMEM, ring of 8 (8 x NT columns) so epilogues overlap the MMAs of later tiles.
+//   Epilogue (2 groups x 4 warps, one TMEM lane quarter per warp, groups alternate tiles), tcgen05.ld 32x32b.x32 -> +bias:
+//            * TMA epilogue (bf16 NHWC outputs at conv resolution): per-warp staging tile in the TMA swizzle pattern,
+//              residual by TMA load, result by TMA tensor store (tc_device.cuh: tc_epilogue_loop_tma);
+//            * direct epilogue (fp32 / upsampled / NCHW-map outputs): residual / ReLU / nearest-upsample replication /
+//              dtype conversion with batched 16-byte global accesses (tc_epilogue_loop).
+// Warp roles (352 threads): warp0 = TMA producer, warps 1-2 = MMA issuers (one elected thread each, alternating tiles, a
+//            private stage ring each; warp1 also allocates TMEM), warps 3-10 = epilogue.
+// Pipelines: per-ring smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), persistent tile loop; launched
+//            with programmatic dependent launch (prologue overlaps the previous conv's tail).
+// The 3x3 stride-1 convs with bf16 outputs normally run on the CTA-pair variant of this kernel (conv_tc_2cta.cu).
 #include <mutex>
 
 #include "conv_tc.cuh"
