@@ -119,7 +119,7 @@ def run_reference(args):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "persons_per_step": persons / max(args.steps, 1),
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_ours(args):
@@ -251,7 +251,7 @@ def run_ours(args):
         v, _ = oracle_fps(4, cores)
         line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
                                 "sample": "4 frames of the cfg2 workload through oracle/romp_oracle.py (torch CPU fp32), after 1 warm-up frame"}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -284,7 +284,7 @@ def run_smpl(args):
     ms = e0.elapsed_time(e1) / args.steps
     peaks = measured_peaks()
     gbs = n * SMPL_BYTES_PER_PERSON / ms / 1e6
-    print(json.dumps({
+    emit(({
         "metric": "persons/sec SMPL forward (verts + 71 joints)", "value": n / ms * 1e3, "unit": "persons/s", "n_gpus": 1,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -338,7 +338,7 @@ def run_bev(args):
     t_e2e = time.perf_counter() - w0
     peaks = measured_peaks()
     fps = B * args.steps / t_dev
-    print(json.dumps({
+    emit(({
         "metric": "frames/sec 512x512 BEV-HRNet32 (whole hot path)", "value": fps, "unit": "frames/s", "n_gpus": 1,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
@@ -364,6 +364,12 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE line (the JSON): library chatter written to file descriptor 1 while we run (NCCL prints
+    # its version banner there on the first communicator) is diverted to stderr; emit() restores the real stdout.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "smpl":
@@ -372,6 +378,20 @@ def main():
         run_bev(args)
     else:
         run_ours(args)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """print the result line on the process's original stdout"""
+    text = json.dumps(line) + "\n"
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, text.encode())
 
 
 if __name__ == "__main__":
