@@ -25,7 +25,10 @@ extern "C" {
 enum { B200ROMP_OK = 0, B200ROMP_EINVAL = -1, B200ROMP_ECUDA = -2, B200ROMP_ENOMEM = -3, B200ROMP_ESTATE = -4 };
 enum { B200ROMP_F32 = 0, B200ROMP_BF16 = 1, B200ROMP_U8 = 2 };
 /* conv engines */
-enum { B200ROMP_ENGINE_AUTO = 0, B200ROMP_ENGINE_SIMT = 1, B200ROMP_ENGINE_TCGEN05 = 2 };
+/* AUTO: bf16 tensors -> tcgen05 (kind::f16), fp32 tensors -> SIMT fp32.  TF32: fp32 tensors -> tcgen05 kind::tf32 (operands
+ * rounded to TF32 with cvt.rna like the reference's cuDNN TF32 convs, fp32 accumulate, fp32 tensors in HBM) where the
+ * shape tiles onto the engine, SIMT fp32 otherwise. */
+enum { B200ROMP_ENGINE_AUTO = 0, B200ROMP_ENGINE_SIMT = 1, B200ROMP_ENGINE_TCGEN05 = 2, B200ROMP_ENGINE_TF32 = 3 };
 
 typedef struct b200romp_net b200romp_net;    /* a conv graph: backbone + heads                          */
 typedef struct b200romp_smpl b200romp_smpl;  /* packed SMPL constants                                     */
@@ -213,6 +216,18 @@ int b200romp_bev_post(const float* betas, const float* verts_smil, const float* 
 /* dst[i] = src[sel[i]] for i < *d_count; rows of row_bytes (multiple of 4) bytes. */
 int b200romp_gather_rows(const void* src, int row_bytes, const int* sel, const int* d_count, int capacity, void* dst,
                          b200romp_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Frame-sharded multi-GPU collection (the reference's DataParallel bookkeeping it stands in for:
+ * romp/lib/maps_utils/result_parser.py:59-64,123-124).  Packs the per-person output arrays of one rank into the
+ * fixed-width record buffer that a single NCCL all-gather ships:
+ *   dst = [1 header row | capacity rows] x dst_row_bytes;  row 1+i = concatenation of srcs[s][i] (seg_bytes[s] bytes each);
+ *   header int32 = {magic 0x0B200B20, count, user0, user1, dst_row_bytes}.
+ * The person count is min(*d_count, capacity) read on the device (d_count may be NULL: then count_host is used), so
+ * neither this call nor the all-gather that follows needs a host synchronisation.  srcs / seg_bytes are HOST arrays
+ * (nseg <= 16) of device pointers / byte counts (multiples of 4). */
+int b200romp_pack_rows(const void* const* srcs, const int* seg_bytes, int nseg, const int* d_count, int count_host,
+                       int capacity, int user0, int user1, void* dst, int dst_row_bytes, b200romp_stream stream);
 
 #ifdef __cplusplus
 }

@@ -38,11 +38,48 @@ def to_torch_sd(sd):
 # ----------------------------------------------------------------------------------------------
 # a2-a5: backbone + head  (simple_romp/romp/model.py)
 # ----------------------------------------------------------------------------------------------
+# Operand rounding of every convolution.  None = the reference's CPU arithmetic (fp32).  "tf32" = what the reference's
+# default GPU path computes (torch.backends.cudnn.allow_tf32 is True and the reference never touches it, so
+# cuDNN runs the convs on TF32 tensor cores): both conv operands rounded to 10 mantissa bits, round-to-nearest with ties
+# away from zero (cvt.rna.tf32.f32), fp32 accumulation, everything else (BatchNorm, residual adds, upsampling) in fp32.
+# This "oracle under TF32-equivalent rounding" gives the error of the reference's own GPU arithmetic against its CPU
+# arithmetic - the yardstick for the tensor-core engines.
+CONV_OPERAND_ROUNDING = None
+
+
+def round_tf32(x):
+    """fp32 -> TF32 (10-bit mantissa), ties away from zero; values stay in fp32 containers."""
+    i = x.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+class conv_rounding:
+    """with conv_rounding("tf32"): ...  - run oracle convolutions with TF32-rounded operands."""
+
+    def __init__(self, mode):
+        assert mode in (None, "tf32")
+        self.mode = mode
+
+    def __enter__(self):
+        global CONV_OPERAND_ROUNDING
+        self.prev, CONV_OPERAND_ROUNDING = CONV_OPERAND_ROUNDING, self.mode
+
+    def __exit__(self, *exc):
+        global CONV_OPERAND_ROUNDING
+        CONV_OPERAND_ROUNDING = self.prev
+
+
+def _conv2d(x, w, b, stride, padding):
+    if CONV_OPERAND_ROUNDING == "tf32":
+        x, w = round_tf32(x), round_tf32(w)
+    return F.conv2d(x, w, b, stride=stride, padding=padding)
+
+
 def conv_bn(sd, conv, bn, x, stride=1, relu=False):
     """Conv2d(k, stride, pad=k//2) [+bias] -> eval BatchNorm2d -> optional ReLU (model.py:49-52,70-72)."""
     w = sd[conv + ".weight"]
     b = sd.get(conv + ".bias")
-    y = F.conv2d(x, w, b, stride=stride, padding=w.shape[-1] // 2)
+    y = _conv2d(x, w, b, stride, w.shape[-1] // 2)
     if bn is not None:
         y = F.batch_norm(y, sd[bn + ".running_mean"], sd[bn + ".running_var"],
                          sd[bn + ".weight"], sd[bn + ".bias"], False, 0.0, BN_EPS)

@@ -14,10 +14,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "lib", "libb200romp.so")
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["net.cu", "conv_simt.cu", "conv_tc.cu", "conv_tc_s2.cu", "conv_stem_tc.cu", "conv_tc_2cta.cu", "parse.cu", "smpl.cu", "project.cu", "bev.cu"]
+SOURCES = ["net.cu", "conv_simt.cu", "conv_tc.cu", "conv_tc_s2.cu", "conv_stem_tc.cu", "conv_tc_2cta.cu", "parse.cu", "smpl.cu", "project.cu", "bev.cu", "pack.cu"]
 
 F32, BF16, U8 = 0, 1, 2
-ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, ENGINE_TF32 = 0, 1, 2, 3
 
 
 class ConvDesc(C.Structure):
@@ -36,11 +36,23 @@ class BevWeights(C.Structure):
         "center_ref", "cam_ref", "coordmap", "anchors", "embed", "w0", "b0", "w1", "b1", "w2", "b2")]
 
 
+NVCC_FLAGS = ["-Xcompiler", "-fPIC", "-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a"]
+OBJ_DIR = os.path.join(HERE, "lib", "obj")
+
+
+def _nvcc():
+    return os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+
+
 def nvcc_command(out_path=LIB_PATH):
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    return [nvcc, "-shared", "-Xcompiler", "-fPIC", "-std=c++17", "-O3", "-lineinfo",
-            "-gencode", "arch=compute_100a,code=sm_100a",
-            "-o", out_path] + [os.path.join(CSRC, s) for s in SOURCES]
+    """The one-shot equivalent of build(): every source -> one sm_100a shared library."""
+    return [_nvcc(), "-shared"] + NVCC_FLAGS + ["-o", out_path] + [os.path.join(CSRC, s) for s in SOURCES]
+
+
+def _headers_mtime():
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hs.append(os.path.join(ROOT, "include", "b200romp.h"))
+    return max(os.path.getmtime(h) for h in hs)
 
 
 def needs_build():
@@ -52,14 +64,36 @@ def needs_build():
 
 
 def build(force=False, verbose=True):
-    """Compile every CUDA source for sm_100a into romp_b200/lib/libb200romp.so (in-tree)."""
+    """Compile every CUDA source for sm_100a (nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo) into
+    romp_b200/lib/libb200romp.so (in-tree).  One object per source, compiled in parallel and reused while the
+    source and the headers are unchanged."""
     if not force and not needs_build():
         return LIB_PATH
-    os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
-    cmd = nvcc_command()
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    hdr_t = _headers_mtime()
+    jobs = []
+    for s in SOURCES:
+        src, obj = os.path.join(CSRC, s), os.path.join(OBJ_DIR, s.replace(".cu", ".o"))
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_t):
+            jobs.append([_nvcc(), "-c"] + NVCC_FLAGS + ["-o", obj, src])
     if verbose:
-        print("[romp_b200] " + " ".join(cmd), file=sys.stderr)
-    subprocess.run(cmd, check=True)
+        for j in jobs:
+            print("[romp_b200] " + " ".join(j), file=sys.stderr)
+
+    def run(cmd):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed: " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+        if verbose and r.stderr.strip():
+            print(r.stderr, file=sys.stderr)
+
+    with ThreadPoolExecutor(max_workers=min(len(jobs) or 1, os.cpu_count() or 4)) as ex:
+        list(ex.map(run, jobs))
+    link = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + [os.path.join(OBJ_DIR, s.replace(".cu", ".o")) for s in SOURCES]
+    if verbose:
+        print("[romp_b200] " + " ".join(link), file=sys.stderr)
+    subprocess.run(link, check=True)
     return LIB_PATH
 
 
@@ -117,6 +151,7 @@ def load():
     _sig(lib.b200romp_bev_regress, i32, vp, vp, vp, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp)
     _sig(lib.b200romp_bev_post, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, fp, f32, f32, f32, vp, vp, vp, vp, vp)
     _sig(lib.b200romp_gather_rows, i32, vp, i32, vp, vp, i32, vp, vp)
+    _sig(lib.b200romp_pack_rows, i32, C.POINTER(vp), ip, i32, vp, i32, i32, i32, i32, vp, i32, vp)
     if lib.b200romp_version() != 100:
         raise RuntimeError("libb200romp.so version mismatch - rebuild")
     _lib = lib
@@ -141,5 +176,5 @@ EXPORTS = [
     "b200romp_smpl_workspace_floats", "b200romp_smpl_forward", "b200romp_project",
     "b200romp_bev_create", "b200romp_bev_destroy", "b200romp_bev_bv_input", "b200romp_bev_center3d",
     "b200romp_bev_parse_workspace_bytes", "b200romp_bev_parse3d", "b200romp_bev_regress", "b200romp_bev_post",
-    "b200romp_gather_rows",
+    "b200romp_gather_rows", "b200romp_pack_rows",
 ]

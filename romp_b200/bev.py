@@ -57,7 +57,7 @@ def bev_settings(input_args=sys.argv[1:]):
     p.add_argument("-t", "--temporal_optimize", action="store_true")
     p.add_argument("-sc", "--smooth_coeff", type=float, default=3.0)
     p.add_argument("--webcam_id", type=int, default=0)
-    p.add_argument("--precision", type=str, default="bf16", choices=["bf16", "fp32"])
+    p.add_argument("--precision", type=str, default="bf16", choices=["bf16", "tf32", "fp32"])
     p.add_argument("--max_batch", type=int, default=32)
     args = p.parse_args(input_args)
     if args.model_id != 2:                                            # bev/main.py:59-63
@@ -89,6 +89,7 @@ class BEV(torch.nn.Module):
         self.tdevice = torch.device("cuda", self.device_index)
         torch.cuda.set_device(self.tdevice)
         self.precision = getattr(s, "precision", "bf16")
+        self._staging = {}
         self.max_batch = B = int(getattr(s, "max_batch", 32))
         if state_dict is None:
             state_dict = torch.load(s.model_path, map_location="cpu")          # bev/main.py:101 (strict=False)
@@ -223,13 +224,22 @@ class BEV(torch.nn.Module):
         if isinstance(frames, np.ndarray):
             frames = torch.from_numpy(frames)
         B = frames.shape[0]
+        # device-resident inputs come from the caller's current stream: order self.stream after it (no host sync)
+        cur = torch.cuda.current_stream(self.tdevice)
+        for t in (frames, center3d_override):
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                if cur != self.stream:
+                    self.stream.wait_stream(cur)
+                t.record_stream(self.stream)
+        key = (frames.dtype, B)
+        if key not in self._staging:                  # stable pointer -> one cached CUDA graph per (dtype, B)
+            self._staging[key] = torch.empty((B, 512, 512, 3), dtype=frames.dtype, device=self.tdevice)
+        fd = self._staging[key]
         with torch.cuda.stream(self.stream):
-            fd = frames.to(self.tdevice, non_blocking=True).contiguous()
+            fd.copy_(frames, non_blocking=True)
             self.run_model(fd, center3d_override)
             self.run_post(B, offsets if offsets is not None else [0, 512, 0, 512, 512, 512], img_max_side)
-        out = self.collect(to_numpy)
-        del fd
-        return out
+        return self.collect(to_numpy)
 
     @torch.no_grad()
     def forward(self, image, signal_ID=0, **kwargs):

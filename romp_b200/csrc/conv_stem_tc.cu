@@ -213,7 +213,7 @@ int tc_stem_prepare(const ConvParams& p, const float* w_oihw, int sm_count, bool
       for (int r = 0; r < 3; ++r)
         for (int s = 0; s < 3; ++s)
           wk[(size_t)co * kStemK + r * 9 + s * 3 + c] = w_oihw[(((size_t)co * 3 + c) * 3 + r) * 3 + s] * (2.0f / 255.0f);
-  int rc = tc_pack_weights(wk.data(), kStemK, 64, 1, kStemNT, &plan->d_wpack, allocs);
+  int rc = tc_pack_weights(wk.data(), kStemK, 64, 1, kStemNT, &plan->d_wpack, allocs, kStemK * 2, 2);
   if (rc) return rc;
   plan->kind = 33;
   plan->cin = 3; plan->cout = 64; plan->nt = kStemNT; plan->stages = kStemStages;

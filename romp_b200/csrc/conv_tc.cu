@@ -32,15 +32,17 @@
 
 namespace b200romp {
 
-template <int KS, int CIN, int NT, bool PER_TAP, int KSPLIT>
+template <int KS, int CIN, int NT, bool PER_TAP, int KSPLIT, int EB>
 struct TcCfg {
   static constexpr int TAPS = KS * KS;
   static constexpr int PAD = KS / 2;
-  // channels per chunk = one swizzle row.  The weight-heavy 3x3 layers (Cin >= 128: 147 KB resident weights) use half
-  // chunks: 4-5 stages of 12 KB instead of 2 of 23 KB, so loads run ahead of the MMAs
-  static constexpr int CW = tc_chunk_width(KS, CIN);
+  // bytes per pixel row in smem (64 or 128 = one swizzle span); channels per chunk = ROWB / EB.  The weight-heavy 3x3 layers
+  // (Cin >= 128: 147 KB resident bf16 weights) use half rows: 4-5 stages of 12 KB instead of 2 of 23 KB, so loads run
+  // ahead of the MMAs
+  static constexpr int ROWB = tc_row_bytes(KS, CIN, EB);
+  static constexpr int CW = ROWB / EB;
   static constexpr int KCH = CIN / CW;
-  static constexpr int ROWB = CW * 2;                  // bytes per pixel row in smem (64 or 128)
+  static constexpr int KSTEPS = ROWB / 32;             // UMMA K steps (32 B = 16 bf16 / 8 tf32) per row
   static constexpr int LAYOUT = ROWB == 128 ? 2 : 4;   // SWIZZLE_128B / SWIZZLE_64B
   static constexpr int HW_ = PER_TAP ? 8 : 8 + 2 * PAD;
   static constexpr int HH = PER_TAP ? 16 : 16 + 2 * PAD;
@@ -51,14 +53,14 @@ struct TcCfg {
   static constexpr int B_BYTES = TAPS * KCH * BTILE;
   static constexpr int ACC = AccCfg<KSPLIT>::ACC;
   static constexpr int TMEM_COLS = tc_tmem_cols(ACC * KSPLIT * NT);
-  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+  static constexpr uint32_t IDESC = tc_idesc(EB, 128, NT);
 };
 
-template <int KS, int CIN, int NT, bool PER_TAP, int KSPLIT>
-__global__ void __launch_bounds__(kTcThreads, 1)
+template <int KS, int CIN, int NT, bool PER_TAP, int KSPLIT, int EB>
+__global__ void __launch_bounds__(tc_threads(EB), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcEpiMaps epi_maps, const ConvParams p,
                const uint8_t* __restrict__ wpack, int tiles_x, int tiles_y, int num_tiles, int stages, int tma_epi) {
-  using Cfg = TcCfg<KS, CIN, NT, PER_TAP, KSPLIT>;
+  using Cfg = TcCfg<KS, CIN, NT, PER_TAP, KSPLIT, EB>;
   constexpr int kAccStages = Cfg::ACC;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -71,14 +73,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   uint64_t* tmem_full = b_full + 1;
   uint64_t* tmem_empty = tmem_full + kAccStages;
   uint64_t* res_bar = tmem_empty + kAccStages;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 3 * kEpiWarps);
+  uint64_t* landed = res_bar + 3 * kEpiWarps;        // EB = 4: "TMA tile landed", consumed by the TF32 rounding warps
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(landed + (EB == 4 ? stages : 0));
   float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr + 2) + 15) & ~(uintptr_t)15);   // 16 B: ld.shared.v4
 
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     for (int i = 0; i < stages; ++i) {
-      mbar_init(&full[i], 1);
+      mbar_init(&full[i], EB == 4 ? kCvtWarps : 1);   // EB = 4: the rounding warps hand the converted tile to the MMA warp
       mbar_init(&empty[i], 1);
+      if (EB == 4) mbar_init(&landed[i], 1);
     }
     mbar_init(b_full, 1);
     for (int i = 0; i < kAccStages; ++i) {
@@ -122,13 +126,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           for (int l = 0; l < Cfg::LOADS_PER_CHUNK; ++l) {
             const int sidx = rbase + stage;
             mbar_wait(&empty[sidx], phase ^ 1);
+            uint64_t* land = EB == 4 ? &landed[sidx] : &full[sidx];
             if (p.debug & 4) {
-              mbar_arrive(&full[sidx]);
+              mbar_arrive(land);
             } else {
-              mbar_arrive_expect_tx(&full[sidx], Cfg::STAGE_PAYLOAD);
+              mbar_arrive_expect_tx(land, Cfg::STAGE_PAYLOAD);
               const int dy = PER_TAP ? l / KS - Cfg::PAD : -Cfg::PAD;
               const int dx = PER_TAP ? l % KS - Cfg::PAD : -Cfg::PAD;
-              tma_load_4d(sA + (size_t)sidx * Cfg::STAGE_BYTES, &tmap, &full[sidx], c * Cfg::CW, x0 + dx, y0 + dy, n, pol);
+              tma_load_4d(sA + (size_t)sidx * Cfg::STAGE_BYTES, &tmap, land, c * Cfg::CW, x0 + dx, y0 + dy, n, pol);
             }
             if (++stage == rsize) { stage = 0; phase ^= 1; }
           }
@@ -164,10 +169,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
               const uint32_t a_tap = PER_TAP ? a_base : a_base + (uint32_t)((r * Cfg::HW_ + s) * Cfg::ROWB);
               const uint32_t b_tap = b_base + (uint32_t)((t * Cfg::KCH + c) * Cfg::BTILE);
 #pragma unroll
-              for (int k = 0; k < Cfg::CW / 16; ++k) {
+              for (int k = 0; k < Cfg::KSTEPS; ++k) {
                 const uint64_t adesc = make_smem_desc(a_tap + k * 32, Cfg::HW_ * Cfg::ROWB, Cfg::LAYOUT);
                 const uint64_t bdesc = make_smem_desc(b_tap + k * 32, 8 * Cfg::ROWB, Cfg::LAYOUT);
-                if (!(p.debug & 2)) umma_bf16(d_tile + (uint32_t)((mma_i % KSPLIT) * NT), adesc, bdesc, Cfg::IDESC, mma_i >= KSPLIT ? 1u : 0u);
+                if (!(p.debug & 2)) umma_any<EB, false>(d_tile + (uint32_t)((mma_i % KSPLIT) * NT), adesc, bdesc, Cfg::IDESC, mma_i >= KSPLIT ? 1u : 0u);
                 ++mma_i;
               }
             }
@@ -178,9 +183,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         umma_commit(&tmem_full[acc]);            // accumulator complete -> epilogue
       }
     }
-  } else if (KSPLIT == 1 && NT == 32 && (tma_epi & kEpiCoalesced)) {   // (instantiated for NT = 32 only: register pressure)
+  } else if (EB == 4 && warp >= kFirstCvtWarp) {
+    // ===================== TF32 rounding warps: landed -> round in place (cvt.rna.tf32) -> full =====================
+    const int cw = warp - kFirstCvtWarp, lane = threadIdx.x & 31;
+    int stage = 0, stage_other = 0;
+    uint32_t phase = 0, phase_other = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int ring = nrings == 2 ? (it & 1) : 0, rbase = tc_ring_base(stages, ring), rsize = tc_ring_size(stages, ring);
+      for (int c = 0; c < Cfg::KCH * Cfg::LOADS_PER_CHUNK; ++c) {
+        const int sidx = rbase + stage;
+        mbar_wait(&landed[sidx], phase);
+        tf32_round_smem(sA + (size_t)sidx * Cfg::STAGE_BYTES, Cfg::STAGE_PAYLOAD, cw, lane);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[sidx]);
+        if (++stage == rsize) { stage = 0; phase ^= 1; }
+      }
+      if (nrings == 2) { const int ts = stage; stage = stage_other; stage_other = ts; const uint32_t tp = phase; phase = phase_other; phase_other = tp; }
+    }
+  } else if (EB == 2 && KSPLIT == 1 && NT == 32 && (tma_epi & kEpiCoalesced)) {   // (instantiated for NT = 32 only: register pressure)
     tc_epilogue_loop_coalesced<NT>(p, tma_epi, epi_smem, tmem_base, tmem_full, tmem_empty, s_bias, tiles_x, per_frame, num_tiles);
-  } else if (KSPLIT == 1 && tma_epi) {
+  } else if (EB == 2 && KSPLIT == 1 && tma_epi) {
     tc_epilogue_loop_tma<NT>(p, epi_maps, tma_epi, epi_smem, res_bar, tmem_base, tmem_full, tmem_empty, s_bias, tiles_x, per_frame,
                              num_tiles);
   } else {
@@ -211,40 +235,44 @@ PFN_encodeTiled tc_get_encode() {
   return fn;
 }
 
-int tc_pack_weights(const float* w_oihw, int cin, int cout, int taps, int nt, void** d_out, std::vector<void*>* allocs, int cw_in) {
-  const int cw = cw_in > 0 ? cw_in : (cin < 64 ? cin : 64), kch = cin / cw, rowb = cw * 2, ntiles = (cout + nt - 1) / nt;
-  std::vector<__nv_bfloat16> img((size_t)ntiles * taps * kch * nt * cw, __float2bfloat16_rn(0.f));
+int tc_pack_weights(const float* w_oihw, int cin, int cout, int taps, int nt, void** d_out, std::vector<void*>* allocs, int rowb, int eb) {
+  // shared-memory image [n-tile][tap][chunk][NT rows x rowb bytes] with the TMA/UMMA XOR swizzle; elements bf16 (eb = 2)
+  // or fp32 rounded to TF32 (eb = 4)
+  const int cw = rowb / eb, kch = cin / cw, ntiles = (cout + nt - 1) / nt, per16 = 16 / eb;
+  std::vector<uint8_t> img((size_t)ntiles * taps * kch * nt * rowb, 0);
   for (int j = 0; j < ntiles; ++j)
     for (int t = 0; t < taps; ++t)
       for (int c = 0; c < kch; ++c) {
-        __nv_bfloat16* tile = img.data() + (((size_t)j * taps + t) * kch + c) * nt * cw;
+        uint8_t* tile = img.data() + (((size_t)j * taps + t) * kch + c) * nt * rowb;
         for (int n = 0; n < nt; ++n)
           for (int k = 0; k < cw; ++k) {
             const int co = j * nt + n, ci = c * cw + k;
             if (co >= cout) continue;                                     // zero rows pad cout up to a multiple of NT
             const float w = w_oihw[((size_t)co * cin + ci) * taps + t];
-            const int chunk16 = k / 8;
+            const int chunk16 = k / per16;
             const int phase = rowb == 128 ? (n & 7) : ((n >> 1) & 3);     // Swizzle<3,4,3> / Swizzle<2,4,3>
-            const size_t byte = (size_t)n * rowb + (size_t)((chunk16 ^ phase) * 16) + (k % 8) * 2;
-            tile[byte / 2] = __float2bfloat16_rn(w);
+            const size_t byte = (size_t)n * rowb + (size_t)((chunk16 ^ phase) * 16) + (k % per16) * eb;
+            if (eb == 2) { const __nv_bfloat16 b = __float2bfloat16_rn(w); memcpy(tile + byte, &b, 2); }
+            else { const float f = tc_round_tf32_host(w); memcpy(tile + byte, &f, 4); }
           }
       }
-  B2R_CUDA_OK(cudaMalloc(d_out, img.size() * sizeof(__nv_bfloat16)));
+  B2R_CUDA_OK(cudaMalloc(d_out, img.size()));
   allocs->push_back(*d_out);
-  B2R_CUDA_OK(cudaMemcpy(*d_out, img.data(), img.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+  B2R_CUDA_OK(cudaMemcpy(*d_out, img.data(), img.size(), cudaMemcpyHostToDevice));
   return B200ROMP_OK;
 }
 
 std::string TcConvPlan::describe() const {
   char buf[96];
-  snprintf(buf, sizeof(buf), " [tc k%d v%d nt%d grid %dx%d smem %d stages %d epi%d]", kind / 10, kind % 10, nt, grid_x, grid_y, smem_bytes, stages, tma_epi);
+  snprintf(buf, sizeof(buf), " [tc%s k%d v%d nt%d grid %dx%d smem %d stages %d epi%d]", eb == 4 ? "-tf32" : "", kind / 10, kind % 10, nt, grid_x, grid_y, smem_bytes, stages, tma_epi);
   return buf;
 }
 
 bool tc_conv_supported(const ConvParams& p, int ksize, int stride) {
   if (stride == 2 && ksize == 3) return tc_s2_supported(p);
   if (stride != 1 || (ksize != 1 && ksize != 3)) return false;
-  if (p.in_dtype != B200ROMP_BF16 || p.input_norm) return false;
+  if ((p.in_dtype != B200ROMP_BF16 && p.in_dtype != B200ROMP_F32) || p.input_norm) return false;   // F32 = the TF32 engine
+  if (p.in_dtype == B200ROMP_F32 && (p.out_dtype != B200ROMP_F32 || (p.res != nullptr && p.res_dtype != B200ROMP_F32))) return false;
   if (p.cin != 32 && p.cin != 64 && p.cin != 128 && p.cin != 256) return false;
   if (p.Hout % 16 != 0 || p.Wout % 8 != 0) return false;
   if (p.in_C % 8 != 0 || p.in_c_off % 8 != 0) return false;             // TMA: 16 B aligned base and strides
@@ -259,9 +287,9 @@ bool tc_conv_supported(const ConvParams& p, int ksize, int stride) {
   return true;
 }
 
-template <int KS, int CIN, int NT, bool PER_TAP, int KSPLIT>
+template <int KS, int CIN, int NT, bool PER_TAP, int KSPLIT, int EB>
 static int launch_inst(const TcConvPlan& plan, const ConvParams& p, cudaStream_t stream, bool set_attr_only) {
-  auto kern = conv_tc_kernel<KS, CIN, NT, PER_TAP, KSPLIT>;
+  auto kern = conv_tc_kernel<KS, CIN, NT, PER_TAP, KSPLIT, EB>;
   if (set_attr_only) {
     B2R_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 /* plans of one instantiation differ (TMA epilogue staging) */));
     return B200ROMP_OK;
@@ -273,7 +301,7 @@ static int launch_inst(const TcConvPlan& plan, const ConvParams& p, cudaStream_t
   const int tiles_x = p.Wout / 8, tiles_y = p.Hout / 16;
   const int num_tiles = tiles_x * tiles_y * p.B;
   dim3 grid(std::min(plan.grid_x, num_tiles), plan.grid_y);
-  B2R_CUDA_OK(tc_launch(kern, grid, kTcThreads, plan.smem_bytes, stream, tm, em, p, reinterpret_cast<const uint8_t*>(plan.d_wpack), tiles_x,
+  B2R_CUDA_OK(tc_launch(kern, grid, tc_threads(EB), plan.smem_bytes, stream, tm, em, p, reinterpret_cast<const uint8_t*>(plan.d_wpack), tiles_x,
                         tiles_y, num_tiles, plan.stages, KSPLIT == 1 ? plan.tma_epi : 0));
   return B200ROMP_OK;
 }
@@ -282,13 +310,19 @@ template <bool PER_TAP>
 static int dispatch(const TcConvPlan& plan, const ConvParams& p, cudaStream_t stream, bool attr) {
   const int ks = plan.kind / 10;
 #define B2R_CASE(K, C, N)                                                                            \
-  if (ks == K && plan.cin == C && plan.nt == N) {                                                   \
-    if (plan.ksplit == 1) return launch_inst<K, C, N, PER_TAP, 1>(plan, p, stream, attr);            \
-    return launch_inst<K, C, N, PER_TAP, tc_ksplit(K * K * (C / 16), N)>(plan, p, stream, attr);      \
+  if (ks == K && plan.cin == C && plan.nt == N && plan.eb == 2) {                                   \
+    if (plan.ksplit == 1) return launch_inst<K, C, N, PER_TAP, 1, 2>(plan, p, stream, attr);         \
+    return launch_inst<K, C, N, PER_TAP, tc_ksplit(K * K * (C / 16), N), 2>(plan, p, stream, attr);   \
   }
+#define B2R_CASE4(K, C, N) \
+  if (ks == K && plan.cin == C && plan.nt == N && plan.eb == 4) return launch_inst<K, C, N, PER_TAP, 1, 4>(plan, p, stream, attr);
   B2R_CASE(3, 32, 32) B2R_CASE(3, 32, 64) B2R_CASE(3, 64, 64) B2R_CASE(3, 128, 64) B2R_CASE(3, 256, 32)
   B2R_CASE(1, 64, 32) B2R_CASE(1, 64, 64) B2R_CASE(1, 128, 32) B2R_CASE(1, 128, 64) B2R_CASE(1, 256, 32)
   B2R_CASE(1, 256, 64) B2R_CASE(1, 32, 64) B2R_CASE(1, 32, 32)
+  // TF32 engine (fp32 tensors): every 1x1 conv; 3x3 only as the fall-back of the CTA-pair engine (odd tile counts)
+  B2R_CASE4(1, 32, 32) B2R_CASE4(1, 32, 64) B2R_CASE4(1, 64, 32) B2R_CASE4(1, 64, 64) B2R_CASE4(1, 128, 32) B2R_CASE4(1, 128, 64)
+  B2R_CASE4(1, 256, 32) B2R_CASE4(1, 256, 64) B2R_CASE4(3, 32, 32) B2R_CASE4(3, 64, 32) B2R_CASE4(3, 64, 64)
+#undef B2R_CASE4
 #undef B2R_CASE
   set_error("conv_tc: no instantiation for k%d cin%d nt%d", ks, plan.cin, plan.nt);
   return B200ROMP_EINVAL;
@@ -342,9 +376,11 @@ int tc_conv_prepare(const ConvParams& p, int ksize, int stride, const float* w_o
     return B200ROMP_ECUDA;
   }
   const bool per_tap = false;   // the per-tap TMA variant (PER_TAP=true) was only the bring-up fallback
-  { const char* e = getenv("B200ROMP_TC_KSPLIT"); plan->ksplit = (e && e[0] == '4') ? 0 : 1; }   /* K-split measured slower: off by default */
+  const int eb = p.in_dtype == B200ROMP_F32 ? 4 : 2;
+  plan->eb = eb;
+  { const char* e = getenv("B200ROMP_TC_KSPLIT"); plan->ksplit = (e && e[0] == '4' && eb == 2) ? 0 : 1; }   /* K-split measured slower: off by default */
   const int taps = ksize * ksize;
-  const int cw = tc_chunk_width(ksize, p.cin), kch = p.cin / cw, rowb = cw * 2;
+  const int rowb = tc_row_bytes(ksize, p.cin, eb), cw = rowb / eb, kch = p.cin / cw;
   // N tile: weights must stay resident next to >= 2 pipeline stages
   int nt = (p.cout % 64 == 0) ? 64 : 32;
   const int hh = per_tap ? 16 : 16 + 2 * (ksize / 2), hw = per_tap ? 8 : 8 + 2 * (ksize / 2);
@@ -353,12 +389,13 @@ int tc_conv_prepare(const ConvParams& p, int ksize, int stride, const float* w_o
   auto bbytes = [&](int n) { return taps * kch * n * rowb; };
   if (bbytes(nt) + 3 * stage_bytes > budget && nt == 64) nt = 32;
   if (bbytes(nt) + 2 * stage_bytes > budget) {
-    set_error("conv_tc: k%d cin%d does not fit shared memory", ksize, p.cin);
+    set_error("conv_tc: k%d cin%d eb%d does not fit shared memory", ksize, p.cin, eb);
     return B200ROMP_EINVAL;
   }
-  // TMA epilogue: needs kEpiWarps staging tiles next to >= 2 stages
+  // TMA epilogue (bf16 tensors only): needs kEpiWarps staging tiles next to >= 2 stages
   int epi_bytes = 0;
-  if (tc_epi_prepare(p, nt, ptrs_final, plan)) {
+  plan->tma_epi = 0;
+  if (eb == 2 && tc_epi_prepare(p, nt, ptrs_final, plan)) {
     const int nb = tc_epi_pick_nbuf(plan->tma_epi, nt, budget - bbytes(nt), stage_bytes);
     if (nb == 0) plan->tma_epi = 0;
     else {
@@ -373,17 +410,17 @@ int tc_conv_prepare(const ConvParams& p, int ksize, int stride, const float* w_o
   plan->grid_y = (p.cout + nt - 1) / nt;
   plan->grid_x = std::max(1, sm_count / plan->grid_y);
   plan->smem_bytes = bbytes(nt) + stages * stage_bytes + epi_bytes + 1024 + 1024;
-  int rcw = tc_pack_weights(w_oihw, p.cin, p.cout, taps, nt, &plan->d_wpack, allocs, cw);
+  int rcw = tc_pack_weights(w_oihw, p.cin, p.cout, taps, nt, &plan->d_wpack, allocs, rowb, eb);
   if (rcw) return rcw;
   // ---- tensor map over the NHWC input: dims (C slice, W, H, N), halo box, OOB -> zeros
   CUtensorMap tm;
   const cuuint64_t gdim[4] = {(cuuint64_t)p.cin, (cuuint64_t)p.Win, (cuuint64_t)p.Hin, (cuuint64_t)p.B};
-  const cuuint64_t gstr[3] = {(cuuint64_t)p.in_C * 2, (cuuint64_t)p.Win * p.in_C * 2, (cuuint64_t)p.Hin * p.Win * p.in_C * 2};
+  const cuuint64_t gstr[3] = {(cuuint64_t)p.in_C * eb, (cuuint64_t)p.Win * p.in_C * eb, (cuuint64_t)p.Hin * p.Win * p.in_C * eb};
   const cuuint32_t box[4] = {(cuuint32_t)cw, (cuuint32_t)hw, (cuuint32_t)hh, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
-  void* base = const_cast<void*>(static_cast<const void*>(static_cast<const __nv_bfloat16*>(p.in) + p.in_c_off));
-  CUresult cr = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                       rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+  void* base = const_cast<uint8_t*>(static_cast<const uint8_t*>(p.in) + (size_t)p.in_c_off * eb);
+  CUresult cr = encode(&tm, eb == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, gdim, gstr, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) {
     set_error("conv_tc: cuTensorMapEncodeTiled failed with %d", (int)cr);

@@ -10,6 +10,7 @@ namespace b200romp {
 struct TcConvPlan {
   int kind = 0;                 // kernel family, 0 = none
   int cin = 0, cout = 0, nt = 0;  // channels, output channels per CTA
+  int eb = 2;                   // operand element bytes: 2 = bf16 (kind::f16), 4 = fp32 storage consumed as TF32 (kind::tf32)
   int grid_x = 0, grid_y = 0, stages = 0;
   int ksplit = 0;               // 1 = single accumulator per tile (bring-up mode), 0 = K-split accumulators
   int smem_bytes = 0;

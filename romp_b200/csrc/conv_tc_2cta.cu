@@ -22,12 +22,13 @@
 
 namespace b200romp {
 
-template <int CIN, int NT>
+template <int CIN, int NT, int EB>
 struct Tc2Cfg {
   static constexpr int KS = 3, TAPS = 9, PAD = 1;
-  static constexpr int CW = tc_chunk_width(3, CIN);
+  static constexpr int ROWB = tc_row_bytes(3, CIN, EB);          // bytes per pixel row of a stage (one swizzle span)
+  static constexpr int CW = ROWB / EB;                           // channels per K chunk
   static constexpr int KCH = CIN / CW;
-  static constexpr int ROWB = CW * 2;
+  static constexpr int KSTEPS = ROWB / 32;                       // UMMA K steps (32 B) per row
   static constexpr int LAYOUT = ROWB == 128 ? 2 : 4;
   static constexpr int HW_ = 10, HH = 18;
   static constexpr int STAGE_PAYLOAD = HH * HW_ * ROWB;
@@ -36,14 +37,14 @@ struct Tc2Cfg {
   static constexpr int B_BYTES = TAPS * KCH * BTILE;
   static constexpr int ACC = AccCfg<1>::ACC;
   static constexpr int TMEM_COLS = tc_tmem_cols(ACC * NT);
-  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((256u >> 4) << 24);
+  static constexpr uint32_t IDESC = tc_idesc(EB, 256, NT);
 };
 
-template <int CIN, int NT>
-__global__ void __launch_bounds__(kTcThreads, 1)
+template <int CIN, int NT, int EB>
+__global__ void __launch_bounds__(tc_threads(EB), 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcEpiMaps epi_maps, const ConvParams p,
                 const uint8_t* __restrict__ wpack, int tiles_x, int tiles_y, int num_tiles, int stages, int tma_epi) {
-  using Cfg = Tc2Cfg<CIN, NT>;
+  using Cfg = Tc2Cfg<CIN, NT, EB>;
   constexpr int kAccStages = Cfg::ACC;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -57,15 +58,19 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   uint64_t* tmem_full = b_peer + 1;
   uint64_t* tmem_empty = tmem_full + kAccStages;
   uint64_t* res_bar = tmem_empty + kAccStages;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 3 * kEpiWarps);
+  uint64_t* landed = res_bar + 3 * kEpiWarps;        // EB = 4: "TMA tile landed" (local), consumed by the TF32 rounding warps
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(landed + (EB == 4 ? stages : 0));
   float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr + 2) + 15) & ~(uintptr_t)15);   // 16 B: ld.shared.v4
 
   const int warp = threadIdx.x >> 5;
   const uint32_t rank = cluster_ctarank();          // 0 = leader
   if (threadIdx.x == 0) {
     for (int i = 0; i < stages; ++i) {
-      mbar_init(&full[i], 1);
+      // EB = 2: the two TMA loads of a pair complete_tx on the leader's full[]; EB = 4: the rounding warps of both
+      // CTAs arrive on it once their CTA's tile is converted
+      mbar_init(&full[i], EB == 4 ? 2 * kCvtWarps : 1);
       mbar_init(&empty[i], 1);
+      if (EB == 4) mbar_init(&landed[i], 1);
     }
     mbar_init(b_full, 1);
     mbar_init(b_peer, 1);
@@ -106,8 +111,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         for (int c = 0; c < Cfg::KCH; ++c) {
           const int sidx = rbase + stage;
           mbar_wait(&empty[sidx], phase ^ 1);
-          if (rank == 0) mbar_arrive_expect_tx(&full[sidx], 2 * Cfg::STAGE_PAYLOAD);      // own tile + the peer's
-          tma_load_4d_2cta(sA + (size_t)sidx * Cfg::STAGE_BYTES, &tmap, &full[sidx], c * Cfg::CW, x0 - 1, y0 - 1, n, pol);
+          if (EB == 4) {
+            mbar_arrive_expect_tx(&landed[sidx], Cfg::STAGE_PAYLOAD);
+            tma_load_4d(sA + (size_t)sidx * Cfg::STAGE_BYTES, &tmap, &landed[sidx], c * Cfg::CW, x0 - 1, y0 - 1, n, pol);
+          } else {
+            if (rank == 0) mbar_arrive_expect_tx(&full[sidx], 2 * Cfg::STAGE_PAYLOAD);      // own tile + the peer's
+            tma_load_4d_2cta(sA + (size_t)sidx * Cfg::STAGE_BYTES, &tmap, &full[sidx], c * Cfg::CW, x0 - 1, y0 - 1, n, pol);
+          }
           if (++stage == rsize) { stage = 0; phase ^= 1; }
         }
         if (nrings == 2) { const int ts = stage; stage = stage_other; stage_other = ts; const uint32_t tp = phase; phase = phase_other; phase_other = tp; }
@@ -147,10 +157,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             const uint32_t a_tap = a_base + (uint32_t)((r * Cfg::HW_ + s) * Cfg::ROWB);
             const uint32_t b_tap = b_base + (uint32_t)((t * Cfg::KCH + c) * Cfg::BTILE);
 #pragma unroll
-            for (int k = 0; k < Cfg::CW / 16; ++k) {
+            for (int k = 0; k < Cfg::KSTEPS; ++k) {
               const uint64_t adesc = make_smem_desc(a_tap + k * 32, Cfg::HW_ * Cfg::ROWB, Cfg::LAYOUT);
               const uint64_t bdesc = make_smem_desc(b_tap + k * 32, 8 * Cfg::ROWB, Cfg::LAYOUT);
-              umma_bf16_2cta(d_tile, adesc, bdesc, Cfg::IDESC, mma_i > 0 ? 1u : 0u);
+              umma_any<EB, true>(d_tile, adesc, bdesc, Cfg::IDESC, mma_i > 0 ? 1u : 0u);
               ++mma_i;
             }
           }
@@ -160,10 +170,31 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         umma_commit_2cta(&tmem_full[acc]);         // both halves of the accumulator complete -> both epilogues
       }
     }
+  } else if (EB == 4 && warp >= kFirstCvtWarp) {
+    // ===================== TF32 rounding warps (both CTAs): landed -> round in place -> full (on the leader) =====================
+    const int cw = warp - kFirstCvtWarp, lane = threadIdx.x & 31;
+    int stage = 0, stage_other = 0;
+    uint32_t phase = 0, phase_other = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int ring = nrings == 2 ? (it & 1) : 0, rbase = tc_ring_base(stages, ring), rsize = tc_ring_size(stages, ring);
+      for (int c = 0; c < Cfg::KCH; ++c) {
+        const int sidx = rbase + stage;
+        mbar_wait(&landed[sidx], phase);
+        tf32_round_smem(sA + (size_t)sidx * Cfg::STAGE_BYTES, Cfg::STAGE_PAYLOAD, cw, lane);
+        fence_proxy_async();                        // generic-proxy writes -> visible to the tensor core's reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&full[sidx], 0);
+        if (++stage == rsize) { stage = 0; phase ^= 1; }
+      }
+      if (nrings == 2) { const int ts = stage; stage = stage_other; stage_other = ts; const uint32_t tp = phase; phase = phase_other; phase_other = tp; }
+    }
+  } else if (EB == 4 || tma_epi == 0) {
+    tc_epilogue_loop<NT, 1, true>(p, tmem_base, tmem_full, tmem_empty, s_bias, tiles_x, per_frame, num_tiles);
   } else {
-    if (NT == 32 && (tma_epi & kEpiCoalesced))
+    if (EB == 2 && NT == 32 && (tma_epi & kEpiCoalesced))
       tc_epilogue_loop_coalesced<NT, true>(p, tma_epi, epi_smem, tmem_base, tmem_full, tmem_empty, s_bias, tiles_x, per_frame, num_tiles);
-    else
+    else if (EB == 2)
       tc_epilogue_loop_tma<NT, true>(p, epi_maps, tma_epi, epi_smem, res_bar, tmem_base, tmem_full, tmem_empty, s_bias, tiles_x,
                                      per_frame, num_tiles);
   }
@@ -176,34 +207,44 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------
-// weights: [ntile][half][tap][chunk][NT/2 rows x ROWB], swizzled by the row index inside the half tile
-static int pack_weights_2cta(const float* w_oihw, int cin, int cout, int nt, int cw, void** d_out, std::vector<void*>* allocs) {
-  const int kch = cin / cw, rowb = cw * 2, ntiles = cout / nt, hn = nt / 2;
-  std::vector<__nv_bfloat16> img((size_t)ntiles * 2 * 9 * kch * hn * cw, __float2bfloat16_rn(0.f));
+// weights: [ntile][half][tap][chunk][NT/2 rows x ROWB], swizzled by the row index inside the half tile; elements are
+// bf16 (eb = 2) or fp32 values rounded to TF32 (eb = 4, ties away from zero like cvt.rna.tf32.f32)
+float tc_round_tf32_host(float w) {
+  uint32_t u;
+  memcpy(&u, &w, 4);
+  if ((u & 0x7F800000u) != 0x7F800000u) u = (u + 0x1000u) & ~0x1FFFu;
+  float r;
+  memcpy(&r, &u, 4);
+  return r;
+}
+static int pack_weights_2cta(const float* w_oihw, int cin, int cout, int nt, int rowb, int eb, void** d_out, std::vector<void*>* allocs) {
+  const int cw = rowb / eb, kch = cin / cw, ntiles = cout / nt, hn = nt / 2, per16 = 16 / eb;
+  std::vector<uint8_t> img((size_t)ntiles * 2 * 9 * kch * hn * rowb, 0);
   for (int j = 0; j < ntiles; ++j)
     for (int h = 0; h < 2; ++h)
       for (int t = 0; t < 9; ++t)
         for (int c = 0; c < kch; ++c) {
-          __nv_bfloat16* tile = img.data() + ((((size_t)j * 2 + h) * 9 + t) * kch + c) * hn * cw;
+          uint8_t* tile = img.data() + ((((size_t)j * 2 + h) * 9 + t) * kch + c) * hn * rowb;
           for (int n = 0; n < hn; ++n)
             for (int k = 0; k < cw; ++k) {
               const int co = j * nt + h * hn + n, ci = c * cw + k;
               const float w = w_oihw[((size_t)co * cin + ci) * 9 + t];
-              const int chunk16 = k / 8;
+              const int chunk16 = k / per16;
               const int phase = rowb == 128 ? (n & 7) : ((n >> 1) & 3);
-              const size_t byte = (size_t)n * rowb + (size_t)((chunk16 ^ phase) * 16) + (k % 8) * 2;
-              tile[byte / 2] = __float2bfloat16_rn(w);
+              const size_t byte = (size_t)n * rowb + (size_t)((chunk16 ^ phase) * 16) + (k % per16) * eb;
+              if (eb == 2) { const __nv_bfloat16 b = __float2bfloat16_rn(w); memcpy(tile + byte, &b, 2); }
+              else { const float f = tc_round_tf32_host(w); memcpy(tile + byte, &f, 4); }
             }
         }
-  B2R_CUDA_OK(cudaMalloc(d_out, img.size() * sizeof(__nv_bfloat16)));
+  B2R_CUDA_OK(cudaMalloc(d_out, img.size()));
   allocs->push_back(*d_out);
-  B2R_CUDA_OK(cudaMemcpy(*d_out, img.data(), img.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+  B2R_CUDA_OK(cudaMemcpy(*d_out, img.data(), img.size(), cudaMemcpyHostToDevice));
   return B200ROMP_OK;
 }
 
-template <int CIN, int NT>
+template <int CIN, int NT, int EB>
 static int tc2_inst(const TcConvPlan& plan, const ConvParams& p, cudaStream_t stream, bool attr) {
-  auto kern = conv_tc2_kernel<CIN, NT>;
+  auto kern = conv_tc2_kernel<CIN, NT, EB>;
   if (attr) {
     B2R_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     return B200ROMP_OK;
@@ -218,7 +259,7 @@ static int tc2_inst(const TcConvPlan& plan, const ConvParams& p, cudaStream_t st
   static const bool pdl = [] { const char* e = getenv("B200ROMP_NO_PDL"); return !(e && e[0] == '1'); }();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
-  cfg.blockDim = dim3(kTcThreads);
+  cfg.blockDim = dim3(tc_threads(EB));
   cfg.dynamicSmemBytes = (size_t)plan.smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute at[2];
@@ -234,11 +275,12 @@ static int tc2_inst(const TcConvPlan& plan, const ConvParams& p, cudaStream_t st
 }
 
 static int tc2_dispatch(const TcConvPlan& plan, const ConvParams& p, cudaStream_t stream, bool attr) {
-#define B2R_C2(C, N) \
-  if (plan.cin == C && plan.nt == N) return tc2_inst<C, N>(plan, p, stream, attr);
-  B2R_C2(32, 32) B2R_C2(64, 64) B2R_C2(128, 64) B2R_C2(256, 64) B2R_C2(256, 32) B2R_C2(32, 64)
+#define B2R_C2(C, N, E) \
+  if (plan.cin == C && plan.nt == N && plan.eb == E) return tc2_inst<C, N, E>(plan, p, stream, attr);
+  B2R_C2(32, 32, 2) B2R_C2(64, 64, 2) B2R_C2(128, 64, 2) B2R_C2(256, 64, 2) B2R_C2(256, 32, 2) B2R_C2(32, 64, 2)
+  B2R_C2(32, 32, 4) B2R_C2(64, 64, 4) B2R_C2(128, 64, 4) B2R_C2(256, 32, 4) B2R_C2(32, 64, 4)
 #undef B2R_C2
-  set_error("conv_tc_2cta: no instantiation for cin%d nt%d", plan.cin, plan.nt);
+  set_error("conv_tc_2cta: no instantiation for cin%d nt%d eb%d", plan.cin, plan.nt, plan.eb);
   return B200ROMP_EINVAL;
 }
 
@@ -247,40 +289,51 @@ static int tc2_dispatch(const TcConvPlan& plan, const ConvParams& p, cudaStream_
 int tc2_try_prepare(const ConvParams& p, int ksize, int stride, const float* w_oihw, int sm_count, bool ptrs_final, TcConvPlan* plan,
                     std::vector<void*>* allocs) {
   static const bool off = [] { const char* e = getenv("B200ROMP_TC_NO_2CTA"); return e && e[0] == '1'; }();
-  if (off || ksize != 3 || stride != 1 || !ptrs_final) return 0;
+  const int eb = p.in_dtype == B200ROMP_F32 ? 4 : 2;
+  if (off || ksize != 3 || stride != 1 || (eb == 2 && !ptrs_final)) return 0;
   if (p.cin != 32 && p.cin != 64 && p.cin != 128 && p.cin != 256) return 0;
   if (p.cout % 32 != 0) return 0;
+  if (eb == 4 && (p.out_nchw || p.pow_channel >= 0)) return 0;          // map outputs stay on the single-CTA kernel
   const int tiles = (p.Wout / 8) * (p.Hout / 16);
   if (tiles % 2 != 0) return 0;                                        // pairs must never split across the tail
   PFN_encodeTiled encode = tc_get_encode();
   if (!encode) return 0;
-  const int cw = tc_chunk_width(3, p.cin), kch = p.cin / cw, rowb = cw * 2;
+  const int rowb = tc_row_bytes(3, p.cin, eb), cw = rowb / eb, kch = p.cin / cw;
   int nt = (p.cout % 64 == 0) ? 64 : 32;
   const int stage_bytes = (18 * 10 * rowb + 1023) / 1024 * 1024;
   const int budget = 227 * 1024 - 1024 - 1024;
   auto bbytes = [&](int n) { return (9 * kch * (n / 2) * rowb + 1023) / 1024 * 1024; };
   plan->ksplit = 1;
-  if (!tc_epi_prepare(p, nt, ptrs_final, plan)) return 0;               // the pair engine only has the TMA epilogue
-  const int nb = tc_epi_pick_nbuf(plan->tma_epi, nt, budget - bbytes(nt), stage_bytes);
-  if (nb == 0) return 0;
-  plan->tma_epi = tc_epi_with_nbuf(plan->tma_epi, nb) | (tc_epi_want_coalesced(nt) ? kEpiCoalesced : 0);
-  const int epi_bytes = tc_epi_total_bytes(plan->tma_epi, nt);
+  plan->eb = eb;
+  int epi_bytes = 0;
+  if (eb == 2) {
+    if (!tc_epi_prepare(p, nt, ptrs_final, plan)) return 0;             // the bf16 pair engine only has the TMA epilogue
+    const int nb = tc_epi_pick_nbuf(plan->tma_epi, nt, budget - bbytes(nt), stage_bytes);
+    if (nb == 0) return 0;
+    plan->tma_epi = tc_epi_with_nbuf(plan->tma_epi, nb) | (tc_epi_want_coalesced(nt) ? kEpiCoalesced : 0);
+    epi_bytes = tc_epi_total_bytes(plan->tma_epi, nt);
+  } else {
+    plan->tma_epi = 0;                                                  // fp32 tensors: direct epilogue
+    if (nt == 64 && bbytes(64) + 4 * stage_bytes > budget) nt = 32;     // fp32 weights are twice the bytes: keep >= 4 stages
+    if (bbytes(nt) + 2 * stage_bytes > budget) return 0;
+  }
   int stages = std::min(8, (budget - bbytes(nt) - epi_bytes) / stage_bytes);
   plan->kind = 34;
   plan->cin = p.cin; plan->cout = p.cout; plan->nt = nt; plan->stages = stages;
   plan->grid_y = p.cout / nt;
   plan->grid_x = std::max(2, (sm_count / plan->grid_y) & ~1);
   plan->smem_bytes = bbytes(nt) + stages * stage_bytes + epi_bytes + 1024 + 1024;
-  int rc = pack_weights_2cta(w_oihw, p.cin, p.cout, nt, cw, &plan->d_wpack, allocs);
+  int rc = pack_weights_2cta(w_oihw, p.cin, p.cout, nt, rowb, eb, &plan->d_wpack, allocs);
   if (rc) return rc;
   CUtensorMap tm;
   const cuuint64_t gdim[4] = {(cuuint64_t)p.cin, (cuuint64_t)p.Win, (cuuint64_t)p.Hin, (cuuint64_t)p.B};
-  const cuuint64_t gstr[3] = {(cuuint64_t)p.in_C * 2, (cuuint64_t)p.Win * p.in_C * 2, (cuuint64_t)p.Hin * p.Win * p.in_C * 2};
+  const cuuint64_t gstr[3] = {(cuuint64_t)p.in_C * eb, (cuuint64_t)p.Win * p.in_C * eb, (cuuint64_t)p.Hin * p.Win * p.in_C * eb};
   const cuuint32_t box[4] = {(cuuint32_t)cw, 10, 18, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
-  const void* base = reinterpret_cast<const __nv_bfloat16*>(p.in) + p.in_c_off;
-  CUresult cr = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
-                       CU_TENSOR_MAP_INTERLEAVE_NONE, rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+  const void* base = reinterpret_cast<const uint8_t*>(p.in) + (size_t)p.in_c_off * eb;
+  CUresult cr = encode(&tm, eb == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base),
+                       gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) {
     set_error("conv_tc_2cta: cuTensorMapEncodeTiled failed with %d", (int)cr);

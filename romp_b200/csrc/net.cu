@@ -358,7 +358,8 @@ int b200romp_net_finalize(b200romp_net* net, int max_batch) {
     const Tensor& ti = net->tensors[op.d.in];
     const Tensor& to = net->tensors[op.d.out];
     const bool stem_like = ti.dtype == B200ROMP_U8 && op.d.cin == 3 && op.d.ksize == 3 && op.d.stride == 2;
-    const bool want_tc = op.d.engine == B200ROMP_ENGINE_TCGEN05 ||
+    const bool want_tf32 = op.d.engine == B200ROMP_ENGINE_TF32 && ti.dtype == B200ROMP_F32;
+    const bool want_tc = op.d.engine == B200ROMP_ENGINE_TCGEN05 || want_tf32 ||
                          (op.d.engine == B200ROMP_ENGINE_AUTO && (ti.dtype == B200ROMP_BF16 || stem_like));
     if (want_tc) {
       ConvParams p;
@@ -382,8 +383,8 @@ int b200romp_net_finalize(b200romp_net* net, int max_batch) {
         rc = tc_stem_prepare(p, op.w_host.data(), net->sm_count, ptrs_final, &op.tc, &net->device_allocs);
         if (rc == B200ROMP_OK) op.engine = B200ROMP_ENGINE_TCGEN05;
         else if (op.d.engine == B200ROMP_ENGINE_TCGEN05) return rc;
-      } else if (params_ok && !stem_like &&
-          tc_conv_supported(p, op.d.ksize, op.d.stride)) {
+      } else if (params_ok && !stem_like && (ti.dtype != B200ROMP_F32 || want_tf32 || op.d.engine == B200ROMP_ENGINE_TCGEN05) &&
+                 tc_conv_supported(p, op.d.ksize, op.d.stride)) {
         rc = tc_conv_prepare(p, op.d.ksize, op.d.stride, op.w_host.data(), net->sm_count, ptrs_final, &op.tc, &net->device_allocs);
         if (rc == B200ROMP_OK) op.engine = B200ROMP_ENGINE_TCGEN05;
         else if (op.d.engine == B200ROMP_ENGINE_TCGEN05) return rc;
@@ -441,7 +442,8 @@ int b200romp_net_run(b200romp_net* net, int batch, b200romp_stream stream_) {
     cudaGraphExec_t exec = nullptr;
     B2R_CUDA_OK(cudaGraphInstantiate(&exec, graph, 0));
     cudaGraphDestroy(graph);
-    if (net->graphs.size() > 16) {   // bound the cache: callers normally cycle through a few buffers
+    if (net->graphs.size() >= 16) {   // bound the cache: callers normally cycle through a few buffers
+      B2R_CUDA_OK(cudaStreamSynchronize(stream));   // an exec may still be running on this stream: never destroy it in flight
       for (auto& kv : net->graphs) cudaGraphExecDestroy(kv.second);
       net->graphs.clear();
     }

@@ -28,11 +28,10 @@ constexpr int kWsFloats = 512;   // per-person scratch: [0,224) features, [224,5
 constexpr int kFeatOff = 0, kAOff = 224;
 constexpr int kMaxBetas = 16;
 
-__constant__ int c_parents[kJ];
-__constant__ int c_depth[kJ];
-
 struct SmplDev {
   int n_betas, K;               // K = n_betas + 207
+  signed char parents[kJ];      // kinematic tree of THIS handle (by value: BEV holds SMPL-A and SMIL handles side by side)
+  signed char depth[kJ];
   const float* v_template;      // [6890*3]
   const float* blend;           // [K][20670]  rows: shapedirs^T then posedirs
   const float* weights;         // [6890][24]
@@ -98,7 +97,7 @@ __global__ void __launch_bounds__(128) smpl_pose_kernel(SmplDev m, const float* 
   // kinematic chain by tree depth (batch_rigid_transform, smpl.py:260-277): G_i = G_parent * [R_i | J_i - J_parent]
   float G[12];
   for (int level = 0; level < 9; ++level) {
-    if (lane < kJ && c_depth[lane] == level) {
+    if (lane < kJ && m.depth[lane] == level) {
       if (level == 0) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
@@ -106,7 +105,7 @@ __global__ void __launch_bounds__(128) smpl_pose_kernel(SmplDev m, const float* 
           G[a * 4 + 3] = Jl[a];
         }
       } else {
-        const int p = c_parents[lane];
+        const int p = m.parents[lane];
         const float t0 = Jl[0] - s_J[warp][p][0], t1 = Jl[1] - s_J[warp][p][1], t2 = Jl[2] - s_J[warp][p][2];
         float P[12];
 #pragma unroll
@@ -317,8 +316,11 @@ b200romp_smpl* b200romp_smpl_create(int device, int n_betas, const float* v_temp
   b200romp_smpl* s = new b200romp_smpl();
   s->device = device;
   const int K = n_betas + 207;
-  bool ok = cudaMemcpyToSymbol(c_parents, par, sizeof(par)) == cudaSuccess &&
-            cudaMemcpyToSymbol(c_depth, depth, sizeof(depth)) == cudaSuccess;
+  bool ok = true;
+  for (int j = 0; j < kJ; ++j) {
+    s->dev.parents[j] = (signed char)par[j];
+    s->dev.depth[j] = (signed char)depth[j];
+  }
   // blend matrix: rows 0..n_betas-1 = shapedirs[:, :, l] flattened, then posedirs
   std::vector<float> blend((size_t)K * 3 * kV);
   for (int l = 0; l < n_betas; ++l)
@@ -383,6 +385,7 @@ int b200romp_smpl_forward(b200romp_smpl* s, const float* betas, int betas_stride
   B2R_REQUIRE(s && betas && thetas && workspace && verts && joints, "smpl_forward: null pointer");
   B2R_REQUIRE(n > 0 && betas_stride >= s->dev.n_betas, "smpl_forward: n must be > 0 and betas_stride >= n_betas");
   cudaStream_t stream = (cudaStream_t)stream_;
+  B2R_CUDA_OK(cudaSetDevice(s->device));
   smpl_pose_kernel<<<(n + 3) / 4, 128, 0, stream>>>(s->dev, betas, betas_stride, thetas, n, d_count, workspace, joints);
   B2R_CUDA_OK(cudaGetLastError());
   dim3 grid((kV + kVT - 1) / kVT, (n + kPT - 1) / kPT);

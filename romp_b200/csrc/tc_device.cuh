@@ -168,6 +168,63 @@ __device__ __forceinline__ void tma_load_4d_2cta(void* dst, const CUtensorMap* m
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// ---- element-size generic forms: EB = 2 -> bf16 operands (kind::f16), EB = 4 -> fp32 storage consumed as TF32 (kind::tf32).
+// All shared-memory geometry of the conv kernels is expressed in BYTES (64 / 128 B swizzle rows, 32 B per UMMA K step =
+// 16 bf16 or 8 tf32 elements), so the TF32 engine is the same pipeline with twice the bytes per channel.
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <int EB, bool CTA2>
+__device__ __forceinline__ void umma_any(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (EB == 2) { if (CTA2) umma_bf16_2cta(d_tmem, adesc, bdesc, idesc, accumulate); else umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate); }
+  else         { if (CTA2) umma_tf32_2cta(d_tmem, adesc, bdesc, idesc, accumulate); else umma_tf32(d_tmem, adesc, bdesc, idesc, accumulate); }
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 | a/b format (1 = BF16, 2 = TF32) | N >> 3 | M >> 4
+__host__ __device__ constexpr uint32_t tc_idesc(int eb, int m, int n) {
+  return (1u << 4) | ((eb == 2 ? 1u : 2u) << 7) | ((eb == 2 ? 1u : 2u) << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// bytes of one shared-memory pixel row (= swizzle span) of a conv's A / B tiles.  The weight-heavy 3x3 layers
+// (Cin >= 128) use half rows: more, smaller pipeline stages next to the resident weight slab.
+__host__ __device__ constexpr int tc_row_bytes(int ksize, int cin, int eb) {
+  return (ksize == 3 && cin >= 128) ? 64 : (cin * eb < 128 ? cin * eb : 128);
+}
+
+// ---- TF32 conversion stage (EB = 4 kernels) -------------------------------------------------------
+// tcgen05.mma kind::tf32 reads fp32 containers and IGNORES the low 13 mantissa bits (truncation).  Measured on the CPU
+// oracle: truncating the activations of the ~100-layer stack biases the maps (mean |err| 1.2e-3 vs 4.8e-4
+// for round-to-nearest), and rounding when a tensor is STORED (so that the truncation becomes exact) doubles the error
+// because the fp32 skip connections get rounded too.  So the TF32 engine does what a cvt.rna.tf32.f32 in front of
+// mma.sync does in the reference's cuDNN/cuBLAS TF32 kernels: kCvtWarps extra warps round every landed A tile in place
+// (shared memory, ties away from zero) between the TMA completion and the MMA issue.  Tensors in HBM stay exact fp32.
+constexpr int kCvtWarps = 4;
+__device__ __forceinline__ uint32_t tf32_rna(uint32_t x) {
+  uint32_t y;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+__device__ __forceinline__ void tf32_round_smem(uint8_t* base, int bytes, int cvt_warp, int lane) {
+  const uint32_t s0 = smem_u32(base);
+  for (int off = (cvt_warp * 32 + lane) * 16; off < bytes; off += kCvtWarps * 32 * 16) {
+    uint32_t a, b, c, d;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(s0 + off));
+    a = tf32_rna(a); b = tf32_rna(b); c = tf32_rna(c); d = tf32_rna(d);
+    asm volatile("st.shared.v4.b32 [%4], {%0, %1, %2, %3};" ::"r"(a), "r"(b), "r"(c), "r"(d), "r"(s0 + off) : "memory");
+  }
+}
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -278,10 +335,12 @@ __host__ __device__ constexpr int tc_num_rings(int stages) { return stages >= 4 
 __host__ __device__ constexpr int tc_ring_size(int stages, int ring) { return tc_num_rings(stages) == 1 ? stages : (stages + 1 - ring) / 2; }
 __host__ __device__ constexpr int tc_ring_base(int stages, int ring) { return ring ? (stages + 1) / 2 : 0; }
 constexpr int kTcThreads = (kFirstEpiWarp + kEpiWarps) * 32;
+constexpr int kFirstCvtWarp = kFirstEpiWarp + kEpiWarps;                 // EB = 4 kernels only: TF32 rounding warps
+__host__ __device__ constexpr int tc_threads(int eb) { return kTcThreads + (eb == 4 ? kCvtWarps * 32 : 0); }
 
 // Epilogue of a persistent tile loop: 2 groups x 4 warps (warps 2..9), group g takes the CTA's tiles g, g+2, ...
 // Each warp owns the TMEM lane quarter (warp id mod 4); thread = one pixel of the 16x8 tile.
-template <int NT, int KSPLIT>
+template <int NT, int KSPLIT, bool CTA2 = false>
 __device__ __forceinline__ void tc_epilogue_loop(const ConvParams& p, uint32_t tmem_base, uint64_t* tmem_full,
                                                  uint64_t* tmem_empty, const float* s_bias, int tiles_x, int per_frame,
                                                  int num_tiles) {
@@ -342,7 +401,10 @@ __device__ __forceinline__ void tc_epilogue_loop(const ConvParams& p, uint32_t t
     }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    if (lane == 0) {
+      if (CTA2) mbar_arrive_cluster(&tmem_empty[acc], 0);     // the pair's leader issues the MMAs of both CTAs
+      else mbar_arrive(&tmem_empty[acc]);
+    }
   }
 }
 
@@ -673,7 +735,8 @@ PFN_encodeTiled tc_get_encode();
 // decides whether the TMA epilogue applies (sets plan->tma_epi and the out/res tensor maps); 0 = direct epilogue
 int tc_epi_prepare(const ConvParams& p, int nt, bool ptrs_final, TcConvPlan* plan);
 // bf16 weight slab in shared-memory-image order [ntile][tap][chunk][NT rows x ROWB] with the TMA/UMMA XOR swizzle
-int tc_pack_weights(const float* w_oihw, int cin, int cout, int taps, int nt, void** d_out, std::vector<void*>* allocs, int cw = 0);
+int tc_pack_weights(const float* w_oihw, int cin, int cout, int taps, int nt, void** d_out, std::vector<void*>* allocs, int rowb, int eb);
+float tc_round_tf32_host(float w);   // fp32 -> TF32, ties away from zero (cvt.rna.tf32.f32)
 // stride-2 3x3 engine (conv_tc_s2.cu)
 bool tc_s2_supported(const ConvParams& p);
 int tc_s2_prepare(const ConvParams& p, const float* w_oihw, int sm_count, bool ptrs_final, TcConvPlan* plan, std::vector<void*>* allocs);

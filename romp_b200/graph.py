@@ -47,10 +47,15 @@ class NetBuilder:
     """Thin typed wrapper over b200romp_net_add_tensor / add_conv that tracks tensor shapes."""
 
     def __init__(self, device: int, precision: str, engine: int = _lib.ENGINE_AUTO):
-        assert precision in ("fp32", "bf16")
+        """precision: "bf16" = bf16 tensors, tcgen05 kind::f16 (fast); "tf32" = fp32 tensors, tcgen05 kind::tf32 with
+        round-to-nearest operand conversion = the arithmetic of the reference's default GPU path (cudnn.allow_tf32);
+        "fp32" = fp32 tensors, SIMT fp32 FMA (strict parity engine)."""
+        assert precision in ("fp32", "bf16", "tf32")
         self.lib = _lib.load()
         self.precision = precision
         self.act = BF16 if precision == "bf16" else F32
+        if precision == "tf32" and engine == _lib.ENGINE_AUTO:
+            engine = _lib.ENGINE_TF32
         self.engine = engine
         self.net = self.lib.b200romp_net_create(device)
         if not self.net:
@@ -93,10 +98,24 @@ class NetBuilder:
         if self.precision == "bf16":
             w = round_bf16(w)      # both engines then see identical bf16-representable weights
         bp = None if b is None else np.ascontiguousarray(b, dtype=np.float32)
+        self.flops_per_frame += 2 * cout * cin * kh * kw * (Ho // up) * (Wo // up)
+        if self.precision == "tf32" and k == 3 and stride == 2 and cin == 256 and res is None and up == 1:
+            # fp32 weights of a 256-channel 3x3 slab do not fit next to the pipeline in shared memory: split K into
+            # two 128-channel convs, the second accumulating onto the first (fp32 intermediate, no rounding in between)
+            H, W, _, _ = self.shape[x]
+            part = self.tensor(Ho, Wo, cout, F32)
+            d0 = ConvDesc(x, in_c_off, part, 0, -1, 0, 0, 128, cout, k, stride, 0, 1, input_norm, -1, d.engine)
+            d1 = ConvDesc(x, in_c_off + 128, out, out_c_off, part, 0, 0, 128, cout, k, stride, int(relu), 1, input_norm,
+                          pow_channel, d.engine)
+            for dd, ws, bb in ((d0, w[:, :128], bp), (d1, w[:, 128:], None)):
+                ws = np.ascontiguousarray(ws)
+                _lib.check(self.lib.b200romp_net_add_conv(
+                    self.net, C.byref(dd), ws.ctypes.data_as(C.POINTER(C.c_float)),
+                    None if bb is None else bb.ctypes.data_as(C.POINTER(C.c_float))), "add_conv")
+            return out
         _lib.check(self.lib.b200romp_net_add_conv(
             self.net, C.byref(d), w.ctypes.data_as(C.POINTER(C.c_float)),
             None if bp is None else bp.ctypes.data_as(C.POINTER(C.c_float))), "add_conv")
-        self.flops_per_frame += 2 * cout * cin * kh * kw * (Ho // up) * (Wo // up)
         return out
 
     def sum(self, base, terms, ups, relu=True, out_dtype=None, name=None):

@@ -52,8 +52,9 @@ def romp_settings(input_args=sys.argv[1:]):
     parser.add_argument("--root_align", type=bool, default=False)
     parser.add_argument("--webcam_id", type=int, default=0)
     # --- additions of this implementation (the reference has no equivalents)
-    parser.add_argument("--precision", type=str, default="bf16", choices=["bf16", "fp32"],
-                        help="conv arithmetic: bf16 tensor cores (fast) or fp32 CUDA cores (parity)")
+    parser.add_argument("--precision", type=str, default="bf16", choices=["bf16", "tf32", "fp32"],
+                        help="conv arithmetic: bf16 tensor cores (fast), tf32 tensor cores on fp32 tensors (the reference's "
+                             "default GPU arithmetic, cudnn.allow_tf32) or fp32 CUDA cores (strict parity)")
     parser.add_argument("--max_batch", type=int, default=64, help="largest batch forward_batch will be given")
     args = parser.parse_args(input_args)
     if not os.path.exists(args.smpl_path):
@@ -239,6 +240,20 @@ class ROMP(torch.nn.Module):
         out["pred_batch_ids"] = src["batch_ids"][:n]
         return out
 
+    def record_layout(self):
+        """Fixed per-person record of this configuration for the sharded path's single all-gather (shard.ShardGather)."""
+        from . import shard
+        return shard.romp_layout(self.calc_smpl, 10)
+
+    def record_fields(self, slot=None):
+        """name -> device tensor [cap, ...] of the slot used by the most recent batch, keyed like record_layout()."""
+        d = (self.slots[self._slot] if slot is None else slot)["dev"]
+        f = {"cam": d["cam"], "smpl_thetas": d["thetas"], "smpl_betas": d["betas"], "center_confs": d["center_confs"],
+             "cam_trans": d["cam_trans"], "center_preds": d["center_preds"], "pred_batch_ids": d["batch_ids"]}
+        if self.calc_smpl:
+            f.update(joints=d["joints"], pj2d_org=d["pj2d_org"], verts=d["verts"])
+        return f, d["count"]
+
     def collect(self, to_numpy=True, slot=None, stream=None):
         """The single host sync of a batch: person count, then D2H of the N valid rows (utils.py:32-41) into pinned
         host mirrors.  The returned numpy arrays are views of those mirrors: valid until the slot is reused, i.e.
@@ -262,39 +277,69 @@ class ROMP(torch.nn.Module):
         return {k: v.numpy() for k, v in self._views(host, n).items()}
 
     # ------------------------------------------------------------------------------------------
+    def _after_producers(self, *tensors):
+        """Device-resident inputs were produced on the caller's current stream; our kernels run on self.stream.  Order
+        them (no host sync) and keep the allocator from recycling the inputs while self.stream still reads them."""
+        cur = torch.cuda.current_stream(self.tdevice)
+        waited = False
+        for t in tensors:
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                if not waited and cur != self.stream:
+                    self.stream.wait_stream(cur)
+                    waited = True
+                t.record_stream(self.stream)
+
+    def _staging(self, slot, dtype, B):
+        """persistent device frame buffer of a slot: a stable pointer keeps the conv graph's CUDA-graph cache at one entry"""
+        key = (dtype, B)
+        if key not in slot["frames"]:
+            slot["frames"][key] = torch.empty((B, 512, 512, 3), dtype=dtype, device=self.tdevice)
+        return slot["frames"][key]
+
     @torch.no_grad()
-    def forward_batch(self, frames, offsets=None, to_numpy=True, center_override=None):
+    def forward_batch(self, frames, offsets=None, to_numpy=True, center_override=None, own=True):
         """frames: [B,512,512,3] RGB uint8/float32 (torch tensor, pinned host or device, or numpy), already
-        padded+resized like img_preprocess.  Returns the reference's dict plus ``pred_batch_ids`` or None."""
+        padded+resized like img_preprocess.  Returns the reference's dict plus ``pred_batch_ids`` or None.
+        Device-resident ``frames`` / ``center_override`` may come straight from a producer on the caller's current
+        stream.  ``own=True`` (default) returns arrays that own their memory; ``own=False`` returns views of the pinned
+        read-back mirrors, valid until the second-next batch."""
         if isinstance(frames, np.ndarray):
             frames = torch.from_numpy(frames)
         B = frames.shape[0]
         self._slot ^= 1
+        slot = self.slots[self._slot]
+        self._after_producers(frames, center_override)
         with torch.cuda.stream(self.stream):
-            fd = frames.to(self.tdevice, non_blocking=True).contiguous()
+            fd = self._staging(slot, frames.dtype, B)
+            fd.copy_(frames, non_blocking=True)
             self.run_maps(fd)
             self.run_post(B, offsets if offsets is not None else [0, 512, 0, 512, 512, 512], center_override)
+            slot["done"].record(self.stream)
         out = self.collect(to_numpy)
-        del fd
+        if out is not None and to_numpy and own:
+            out = {k: np.array(v) for k, v in out.items()}
         return out
 
     @torch.no_grad()
     def forward_batches(self, batches, offsets=None, center_override=None, to_numpy=True):
         """Pipelined streaming over an iterable of host frame batches (video): yields one result dict (or None) per
         batch, in order.  H2D of batch i+1 (copy stream) and D2H of batch i-1 (read-back stream) overlap the
-        kernels of batch i; the only host waits are on the person-count event of an already finished batch."""
+        kernels of batch i; the host waits only for the H2D copy of the batch it just handed over (so a caller may
+        refill one pinned buffer in a decode loop) and for the person count of an already finished batch.  With
+        ``to_numpy=True`` the yielded arrays are views of pinned mirrors, valid until the second-next batch is yielded."""
         off = offsets if offsets is not None else [0, 512, 0, 512, 512, 512]
         pending = None
+        self._after_producers(center_override)
         for frames in batches:
             if isinstance(frames, np.ndarray):
                 frames = torch.from_numpy(frames)
             B = frames.shape[0]
             self._slot ^= 1
             slot = self.slots[self._slot]
-            key = (frames.dtype, B)
-            if key not in slot["frames"]:
-                slot["frames"][key] = torch.empty((B, 512, 512, 3), dtype=frames.dtype, device=self.tdevice)
-            fd = slot["frames"][key]
+            fd = self._staging(slot, frames.dtype, B)
+            if frames.is_cuda:
+                self.copy_stream.wait_stream(torch.cuda.current_stream(self.tdevice))
+                frames.record_stream(self.copy_stream)
             with torch.cuda.stream(self.copy_stream):
                 self.copy_stream.wait_event(slot["done"])          # the slot's previous kernels no longer read fd
                 fd.copy_(frames, non_blocking=True)
@@ -304,6 +349,8 @@ class ROMP(torch.nn.Module):
                 self.run_maps(fd)
                 self.run_post(B, off, center_override, slot)
                 slot["done"].record(self.stream)
+            if not frames.is_cuda:
+                slot["h2d"].synchronize()     # the caller may refill its (single) host buffer as soon as we yield / pull the next batch
             if pending is not None:
                 yield self._read_back(pending, to_numpy)
             pending = slot
@@ -323,7 +370,7 @@ class ROMP(torch.nn.Module):
             print("None person detected")                                       # post_parser.py:139
             return None
         out.pop("pred_batch_ids")
-        return {k: np.array(v) for k, v in out.items()}                          # own the memory like the reference
+        return out                                                               # arrays own their memory like the reference's
 
 
 default_settings = None   # the reference evaluates romp_settings([]) at import (main.py:62); we do not

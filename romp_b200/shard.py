@@ -1,19 +1,64 @@
 """Frame-sharded multi-GPU execution.
 
 Frames are independent, so rank r simply runs the whole hot path on its contiguous slice of the batch; no
-collective is needed to compute.  The single collective is the all-gather that *collects* the per-person
-outputs: one all_gather of the person counts, then one padded all_gather of a packed float record and one of
-a packed int64 record.  ``pred_batch_ids`` are offset by the rank's first frame (the reference does the same
-bookkeeping for nn.DataParallel: romp/lib/maps_utils/result_parser.py:59-64).
+collective is needed to compute.  The single collective is the all-gather that *collects* the per-person outputs.
+
+Design (round 2):
+* The per-person record has a FIXED layout that follows from the model configuration (ROMP / BEV, calc_smpl, number of
+  betas) - never from the data - so every rank knows it even when its shard detected nobody.  The sequence of
+  collectives therefore never depends on a rank-local condition.
+* Every rank packs ``[header row | rows]`` into a persistent send buffer with one kernel (``b200romp_pack_rows``; the
+  person count is read on the device) and ONE ``all_gather_into_tensor`` ships ``1 + rows_hint`` rows per rank.  The
+  header carries the rank's count and first frame, so no separate count exchange and no host synchronisation sit in
+  front of the collective.  ``rows_hint`` is a host-side upper bound (previous step's maximum with slack); if a rank
+  overflows it, every rank sees that in the gathered headers and all of them repeat the gather with the exact maximum
+  (rare slow path, collectively decided).
+* ``pred_batch_ids`` are offset by the rank's first frame on unpack (the reference does the same bookkeeping for
+  nn.DataParallel: romp/lib/maps_utils/result_parser.py:59-64).
+* Each rank reads back ITS OWN shard to its host (``ROMP.forward_batches``); the gathered records stay on the device
+  unless a caller asks for them (``result(to_numpy=True)``).
+
+On a non-CUDA backend (the world-size-2 ``gloo`` tests of the host logic) the same code runs on CPU tensors with a
+torch implementation of the pack step.
 """
 from __future__ import annotations
+
+import ctypes as C
 
 import numpy as np
 import torch
 import torch.distributed as dist
 
-FLOAT_KEYS = ["cam", "smpl_thetas", "smpl_betas", "center_confs", "cam_trans", "joints", "pj2d_org", "verts"]
-INT_KEYS = ["center_preds", "pred_batch_ids"]
+MAGIC = 0x0B200B20
+HEADER_WORDS = 8
+
+
+class RecordLayout:
+    """Ordered fields (name, per-person shape, torch dtype) -> byte offsets inside one fixed-width record."""
+
+    def __init__(self, fields):
+        self.fields = [(n, tuple(s), d) for n, s, d in fields]
+        self.offsets, off = [], 0
+        for _, shp, dt in self.fields:
+            nbytes = int(np.prod(shp, dtype=np.int64)) * torch.empty(0, dtype=dt).element_size() if len(shp) else torch.empty(0, dtype=dt).element_size()
+            assert nbytes % 4 == 0
+            self.offsets.append((off, nbytes))
+            off += nbytes
+        self.row_bytes = max(32, (off + 15) // 16 * 16)
+
+    def __eq__(self, other):
+        return isinstance(other, RecordLayout) and self.fields == other.fields
+
+
+def romp_layout(calc_smpl=True, n_betas=10, n_verts=6890):
+    """Record of ROMP.forward's output dict + pred_batch_ids."""
+    f32, i64 = torch.float32, torch.int64
+    fields = [("cam", (3,), f32), ("smpl_thetas", (72,), f32), ("smpl_betas", (n_betas,), f32), ("center_confs", (1,), f32),
+              ("cam_trans", (3,), f32)]
+    if calc_smpl:
+        fields += [("joints", (71, 3), f32), ("pj2d_org", (71, 2), f32), ("verts", (n_verts, 3), f32)]
+    fields += [("center_preds", (2,), i64), ("pred_batch_ids", (), i64)]
+    return RecordLayout(fields)
 
 
 def shard_range(total_frames: int, rank: int, world: int):
@@ -23,166 +68,172 @@ def shard_range(total_frames: int, rank: int, world: int):
     return start, start + base + (1 if rank < rem else 0)
 
 
-def pack(out, frame_offset, device):
-    """dict (or None) -> (float record [n, F], int record [n, 3], layout)."""
-    if out is None:
-        return torch.zeros(0, 0, device=device), torch.zeros(0, 3, dtype=torch.int64, device=device), None
-    t = {k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v).to(device) for k, v in out.items()}
-    n = t["cam"].shape[0]
-    fkeys = [k for k in FLOAT_KEYS if k in t]
-    layout = [(k, tuple(t[k].shape[1:])) for k in fkeys]
-    frec = torch.cat([t[k].reshape(n, -1).float() for k in fkeys], 1)
-    irec = torch.cat([t["center_preds"].reshape(n, 2), (t["pred_batch_ids"] + frame_offset).reshape(n, 1)], 1)
-    return frec.contiguous(), irec.contiguous(), layout
+def _as_tensor(v, device):
+    t = torch.from_numpy(v) if isinstance(v, np.ndarray) else v
+    return t.to(device)
 
 
-def unpack(frec, irec, layout):
-    out, col = {}, 0
-    n = frec.shape[0]
-    for k, shp in layout:
-        w = int(np.prod(shp)) if len(shp) else 1
-        out[k] = frec[:, col:col + w].reshape((n,) + shp)
-        col += w
-    out["center_preds"] = irec[:, :2]
-    out["pred_batch_ids"] = irec[:, 2]
-    out["global_orient"] = out["smpl_thetas"][:, :3]
-    out["body_pose"] = out["smpl_thetas"][:, 3:]
+def pack_rows(layout: RecordLayout, fields: dict, count, frame_offset: int, dst: torch.Tensor, stream=None):
+    """dst uint8 [1 + capacity, row_bytes] <- header + records.  `count`: int, or int32 device tensor on CUDA.
+    CUDA tensors: one b200romp_pack_rows launch (no host sync); CPU tensors (gloo tests): torch copies."""
+    cap = dst.shape[0] - 1
+    if dst.is_cuda:
+        from . import _lib
+        lib = _lib.load()
+        n = len(layout.fields)
+        srcs, sizes = (C.c_void_p * n)(), (C.c_int * n)()
+        for i, ((name, _, dt), (_, nbytes)) in enumerate(zip(layout.fields, layout.offsets)):
+            t = fields[name]
+            assert t.is_cuda and t.is_contiguous() and t.dtype == dt, name
+            srcs[i], sizes[i] = t.data_ptr(), nbytes
+        dcount = count if isinstance(count, torch.Tensor) else None
+        st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        _lib.check(lib.b200romp_pack_rows(srcs, sizes, n, None if dcount is None else C.c_void_p(dcount.data_ptr()),
+                                          0 if dcount is not None else int(count), cap, int(frame_offset), 0,
+                                          C.c_void_p(dst.data_ptr()), layout.row_bytes, C.c_void_p(st)), "pack_rows")
+        return
+    n = int(count)
+    assert n <= cap
+    hdr = torch.zeros(HEADER_WORDS, dtype=torch.int32)
+    hdr[0], hdr[1], hdr[2], hdr[4] = MAGIC, n, int(frame_offset), layout.row_bytes
+    dst[0, :HEADER_WORDS * 4] = hdr.view(torch.uint8)
+    for (name, _, dt), (off, nbytes) in zip(layout.fields, layout.offsets):
+        if n:
+            src = _as_tensor(fields[name], dst.device)[:n].to(dt).contiguous().reshape(n, -1)
+            dst[1:1 + n, off:off + nbytes] = src.view(torch.uint8).reshape(n, nbytes)
+
+
+def unpack_rows(layout: RecordLayout, rows: torch.Tensor, frame_offsets: torch.Tensor):
+    """rows uint8 [n, row_bytes] (+ per-row first-frame offsets, int64 [n]) -> output dict of tensors."""
+    n = rows.shape[0]
+    out = {}
+    for (name, shp, dt), (off, nbytes) in zip(layout.fields, layout.offsets):
+        out[name] = rows[:, off:off + nbytes].contiguous().view(dt).reshape((n,) + shp)
+    out["pred_batch_ids"] = out["pred_batch_ids"] + frame_offsets.to(out["pred_batch_ids"].device)
+    if "smpl_thetas" in out:
+        out["global_orient"], out["body_pose"] = out["smpl_thetas"][:, :3], out["smpl_thetas"][:, 3:]
     return out
 
 
-def all_gather_outputs(out, frame_offset: int, world: int, to_numpy: bool = True, group=None):
-    """All ranks end up with the outputs of every rank, ordered by (global frame asc, score desc)."""
-    backend = dist.get_backend(group)
-    device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
-    frec, irec, layout = pack(out, frame_offset, device)
-    n = torch.tensor([frec.shape[0], frec.shape[1]], dtype=torch.int64, device=device)
-    counts = torch.zeros(world * 2, dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(counts, n, group=group)
-    counts = counts.cpu().view(world, 2)
-    nmax, width = int(counts[:, 0].max()), int(counts[:, 1].max())
-    if nmax == 0:
-        return None
-    if layout is None and width == DEFAULT_WIDTH:
-        layout = DEFAULT_LAYOUT                       # a rank without persons still knows the standard record
-    widths = set(int(w) for w in counts[:, 1].tolist() if int(w) > 0)
-    if layout is None or len(widths) > 1:             # unusual key set: agree on it explicitly (pickled, slow path)
-        layouts = [None] * world
-        dist.all_gather_object(layouts, layout, group=group)
-        layout = next(l for l in layouts if l is not None)
-    fpad = torch.zeros(nmax, width, device=device)
-    ipad = torch.zeros(nmax, 3, dtype=torch.int64, device=device)
-    if frec.shape[0]:
-        fpad[:frec.shape[0]] = frec
-        ipad[:irec.shape[0]] = irec
-    fall = torch.empty(world * nmax, width, device=device)
-    iall = torch.empty(world * nmax, 3, dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(fall, fpad, group=group)
-    dist.all_gather_into_tensor(iall, ipad, group=group)
-    ntot = int(counts[:, 0].sum())
-    if not to_numpy:
-        keep = torch.cat([torch.arange(r * nmax, r * nmax + int(counts[r, 0])) for r in range(world)]).to(device)
-        return unpack(fall[keep], iall[keep], layout)
-    # D2H of the valid rows of every rank's slab into cached pinned mirrors, then host-side views
-    fh, ih = _pinned("f", ntot, width, torch.float32), _pinned("i", ntot, 3, torch.int64)
-    row = 0
-    for r in range(world):
-        c = int(counts[r, 0])
-        if c:
-            fh[row:row + c].copy_(fall[r * nmax:r * nmax + c], non_blocking=True)
-            ih[row:row + c].copy_(iall[r * nmax:r * nmax + c], non_blocking=True)
-            row += c
-    if device.type == "cuda":
-        torch.cuda.current_stream().synchronize()
-    return {k: v.numpy() for k, v in unpack(fh[:ntot], ih[:ntot], layout).items()}
+class ShardGather:
+    """The collective of the frame-sharded path, pipelined for a stream of steps.
 
-
-class GatherPipeline:
-    """Pipelined all_gather_outputs for a stream of steps (the multi-GPU `forward_batches` loop).
-
-    submit() enqueues pack + the padded NCCL all-gathers + the device->host copies of the gathered rows on a side stream
-    and returns at once (only the tiny person-count exchange is synchronous); result() of the PREVIOUS step is collected
-    while the current step computes.  Host mirrors are double-buffered, so a result stays valid until the submit after
-    the next.  `host_rank`: rank that wants numpy results (None = every rank); other ranks only take part in the
-    collective and get None from result().  On a non-CUDA backend (gloo tests) everything runs synchronously.
+    submit() enqueues pack + ONE all-gather on a side stream (after the caller's current stream) and returns at once
+    without any host synchronisation; result() of an earlier step is collected while later steps compute.  Send /
+    receive buffers are persistent and double-buffered (a result stays valid until the second-next submit).
     """
 
-    def __init__(self, world: int, group=None, host_rank=None):
-        self.world, self.group, self.host_rank = world, group, host_rank
+    def __init__(self, world: int, layout: RecordLayout, capacity: int, group=None, rows_hint: int = 64):
+        self.world, self.layout, self.capacity, self.group = world, layout, int(capacity), group
         self.cuda = dist.get_backend(group) == "nccl"
+        self.device = torch.device("cuda", torch.cuda.current_device()) if self.cuda else torch.device("cpu")
         self.stream = torch.cuda.Stream() if self.cuda else None
+        self.rows_hint = max(1, min(int(rows_hint), self.capacity))
+        rb = layout.row_bytes
+        self.send = [torch.zeros(1 + self.capacity, rb, dtype=torch.uint8, device=self.device) for _ in range(2)]
+        self.recv = [None, None]
         self.slot = 0
+        self.collectives = 0           # all-gathers issued so far (tests / gpu_launches accounting)
 
-    def submit(self, out, frame_offset: int):
-        if not self.cuda:
-            return ("done", all_gather_outputs(out, frame_offset, self.world, True, self.group))
-        rank = dist.get_rank(self.group)
-        want_host = self.host_rank is None or rank == self.host_rank
-        device = torch.device("cuda", torch.cuda.current_device())
-        frec, irec, layout = pack(out, frame_offset, device)
-        n = torch.tensor([frec.shape[0], frec.shape[1]], dtype=torch.int64, device=device)
-        counts = torch.zeros(self.world * 2, dtype=torch.int64, device=device)
-        dist.all_gather_into_tensor(counts, n, group=self.group)
-        counts = counts.cpu().view(self.world, 2)                  # the one synchronisation point (16 B per rank)
-        nmax, width = int(counts[:, 0].max()), int(counts[:, 1].max())
-        if nmax == 0:
-            return ("done", None)
-        if layout is None or width != DEFAULT_WIDTH:
-            # unusual key set: fall back to the synchronous path (agrees on the layout explicitly)
-            return ("done", all_gather_outputs(out, frame_offset, self.world, True, self.group))
-        ready = torch.cuda.Event()
-        ready.record()
+    def _recv(self, slot, rows):
+        need = self.world * (1 + rows)
+        buf = self.recv[slot]
+        if buf is None or buf.shape[0] < need:
+            buf = self.recv[slot] = torch.empty(need + self.world * max(16, rows // 4), self.layout.row_bytes, dtype=torch.uint8, device=self.device)
+        return buf[:need]
+
+    def _send(self, slot, rows):
+        buf = self.send[slot]
+        if buf.shape[0] < 1 + rows:      # only the one-shot form (rank-local capacity) ever grows a send buffer
+            big = torch.zeros(1 + rows, self.layout.row_bytes, dtype=torch.uint8, device=self.device)
+            big[:buf.shape[0]] = buf
+            buf = self.send[slot] = big
+        return buf[:1 + rows]
+
+    def _gather(self, slot, rows):
+        recv = self._recv(slot, rows)
+        dist.all_gather_into_tensor(recv.view(-1), self._send(slot, rows).view(-1), group=self.group)
+        self.collectives += 1
+        return recv
+
+    def submit(self, fields: dict, count, frame_offset: int, rows_hint: int | None = None):
+        """fields: name -> tensor [cap, ...] (device tensors of the ROMP slot, or CPU tensors under gloo);
+        count: python int or int32 device tensor.  Returns a handle for result()."""
         slot, self.slot = self.slot, self.slot ^ 1
-        with torch.cuda.stream(self.stream):
-            self.stream.wait_event(ready)
-            fpad = torch.zeros(nmax, width, device=device)
-            ipad = torch.zeros(nmax, 3, dtype=torch.int64, device=device)
-            if frec.shape[0]:
-                fpad[:frec.shape[0]] = frec
-                ipad[:irec.shape[0]] = irec
-            fall = torch.empty(self.world * nmax, width, device=device)
-            iall = torch.empty(self.world * nmax, 3, dtype=torch.int64, device=device)
-            dist.all_gather_into_tensor(fall, fpad, group=self.group)
-            dist.all_gather_into_tensor(iall, ipad, group=self.group)
-            ntot = int(counts[:, 0].sum())
-            fh = ih = None
-            if want_host:
-                fh, ih = _pinned(("f", slot), ntot, width, torch.float32), _pinned(("i", slot), ntot, 3, torch.int64)
-                row = 0
-                for r in range(self.world):
-                    c = int(counts[r, 0])
-                    if c:
-                        fh[row:row + c].copy_(fall[r * nmax:r * nmax + c], non_blocking=True)
-                        ih[row:row + c].copy_(iall[r * nmax:r * nmax + c], non_blocking=True)
-                        row += c
-            done = torch.cuda.Event()
-            done.record(self.stream)
-        for t in (frec, irec, fpad, ipad, fall, iall):
-            t.record_stream(self.stream)
-        return ("pending", done, fh, ih, ntot, (fall, iall))
+        rows = min(self.capacity, max(1, int(self.rows_hint if rows_hint is None else rows_hint)))
+        if self.cuda:
+            ready = torch.cuda.Event()
+            ready.record()
+            with torch.cuda.stream(self.stream):
+                self.stream.wait_event(ready)
+                pack_rows(self.layout, fields, count, frame_offset, self.send[slot], self.stream.cuda_stream)
+                recv = self._gather(slot, rows)
+                done = torch.cuda.Event()
+                done.record(self.stream)
+            for t in fields.values():
+                if isinstance(t, torch.Tensor) and t.is_cuda:
+                    t.record_stream(self.stream)
+        else:
+            pack_rows(self.layout, fields, count, frame_offset, self.send[slot])
+            recv, done = self._gather(slot, rows), None
+        return dict(slot=slot, rows=rows, recv=recv, done=done)
 
-    def result(self, handle):
-        if handle[0] == "done":
-            return handle[1]
-        _, done, fh, ih, ntot, _keep = handle
-        done.synchronize()
-        if fh is None:
+    def wait(self, handle, stream=None):
+        """Make `stream` (default: the current stream) wait for the gather of `handle` - device-side join, no host sync."""
+        if handle["done"] is not None:
+            (torch.cuda.current_stream() if stream is None else stream).wait_event(handle["done"])
+
+    def result(self, handle, to_numpy=False):
+        """Every rank's persons in global frame order as a dict of tensors on the gather device (or numpy arrays),
+        or None when nobody was detected anywhere.  The one host synchronisation: the gathered headers."""
+        slot, rows, recv = handle["slot"], handle["rows"], handle["recv"]
+        if handle["done"] is not None:
+            handle["done"].synchronize()
+        rb = self.layout.row_bytes
+        per = 1 + rows
+        hdr = recv.view(self.world, per, rb)[:, 0, :HEADER_WORDS * 4].contiguous().view(torch.int32).cpu()
+        assert bool((hdr[:, 0] == MAGIC).all()) and bool((hdr[:, 4] == rb).all()), "record layout differs between ranks"
+        counts, offsets = hdr[:, 1].tolist(), hdr[:, 2].tolist()
+        nmax = max(counts)
+        self.rows_hint = min(self.capacity, max(16, int(nmax * 1.25) + 8))      # next step's bound
+        if nmax > rows:
+            # some rank held more persons than the hint: every rank sees the same headers, so all of them repeat the
+            # gather with the exact maximum (the send buffers still hold the full pack)
+            if self.cuda:
+                with torch.cuda.stream(self.stream):
+                    recv = self._gather(slot, nmax)
+                    self.stream.synchronize()
+            else:
+                recv = self._gather(slot, nmax)
+            rows, per = nmax, 1 + nmax
+        if nmax == 0:
             return None
-        return {k: v.numpy() for k, v in unpack(fh[:ntot], ih[:ntot], DEFAULT_LAYOUT).items()}
+        v = recv.view(self.world, per, rb)
+        parts = [v[r, 1:1 + c] for r, c in enumerate(counts) if c]
+        offs = torch.cat([torch.full((c,), o, dtype=torch.int64) for c, o in zip(counts, offsets) if c])
+        out = unpack_rows(self.layout, torch.cat(parts, 0), offs)
+        if to_numpy:
+            out = {k: t.cpu().numpy() for k, t in out.items()}
+        return out
 
 
-DEFAULT_LAYOUT = [("cam", (3,)), ("smpl_thetas", (72,)), ("smpl_betas", (10,)), ("center_confs", (1,)), ("cam_trans", (3,)),
-                  ("joints", (71, 3)), ("pj2d_org", (71, 2)), ("verts", (6890, 3))]
-DEFAULT_WIDTH = sum(int(np.prod(s)) for _, s in DEFAULT_LAYOUT)
-_PIN = {}
-
-
-def _pinned(tag, rows, width, dtype):
-    """Grow-only pinned host mirror (valid until the next gather that needs it)."""
-    key = (tag, width, dtype)
-    buf = _PIN.get(key)
-    if buf is None or buf.shape[0] < rows:
-        buf = torch.empty(max(rows, 64) * 2, width, dtype=dtype)
-        if torch.cuda.is_available():
-            buf = buf.pin_memory()
-        _PIN[key] = buf
-    return buf
+def all_gather_outputs(out, frame_offset: int, world: int, to_numpy: bool = True, group=None, layout: RecordLayout | None = None,
+                       rows_hint: int = 64):
+    """One-shot convenience form: `out` is a result dict of ROMP.forward_batch (numpy or tensors) or None.  All ranks
+    end up with the outputs of every rank, ordered by (global frame asc, score desc).  `layout` defaults to the ROMP
+    record matching `out` (a rank whose `out` is None must pass the layout of its configuration unless it is the
+    default one) - it is never negotiated at run time.  `rows_hint` must be the same on every rank."""
+    if layout is None:
+        if out is None:
+            layout = romp_layout()
+        else:
+            nb = int(np.asarray(out["smpl_betas"]).shape[1])
+            layout = romp_layout("verts" in out, nb, int(np.asarray(out["verts"]).shape[1]) if "verts" in out else 6890)
+    n = 0 if out is None else int(np.asarray(out["cam"]).shape[0]) if not isinstance(out["cam"], torch.Tensor) else int(out["cam"].shape[0])
+    g = ShardGather(world, layout, capacity=max(n, rows_hint), group=group, rows_hint=rows_hint)
+    fields = {}
+    if out is not None:
+        fields = {name: _as_tensor(out[name], g.device).to(dt).contiguous() for name, _, dt in layout.fields}
+    else:
+        fields = {name: torch.zeros((1,) + shp, dtype=dt, device=g.device) for name, shp, dt in layout.fields}
+    return g.result(g.submit(fields, n, frame_offset), to_numpy=to_numpy)

@@ -237,6 +237,35 @@ def plant_centers(batch: int, seed: int = 0, kmin: int = 1, kmax: int = 10, size
 # --------------------------------------------------------------------------------------
 # BEV head parameters (simple_romp/bev/model.py:104-187): enumeration + synthetic values
 # --------------------------------------------------------------------------------------
+def nms_peaks(center_maps):
+    """Values and flat indices of the 5x5 local maxima of [B,1,S,S] maps (CenterMap.nms, post_parser.py:50-54), per frame."""
+    cm = np.asarray(center_maps, np.float32)[:, 0]
+    B, S, _ = cm.shape
+    pad = np.full((B, S + 4, S + 4), -np.inf, np.float32)
+    pad[:, 2:-2, 2:-2] = cm
+    mx = np.max(np.stack([pad[:, dy:dy + S, dx:dx + S] for dy in range(5) for dx in range(5)]), 0)
+    return [(cm[b][mx[b] == cm[b]], np.flatnonzero((mx[b] == cm[b]).ravel())) for b in range(B)]
+
+
+def calibrate_center_head(sd, center_maps, max_per_frame: float = 10.0, thresh: float = 0.25):
+    """Synthetic weights detect nobody (the raw center head hovers around 0), so the natural-detection tests and benches
+    calibrate the LAST layer of the center head, ``final_layers.2.2`` (Conv2d 64->1 with bias, model.py:455-468): its
+    bias is shifted so that between 1 and ``max_per_frame`` NMS peaks per frame (on average) of ``center_maps`` (the
+    fp32 maps the un-shifted weights produce on the calibration frames) exceed ``thresh``.  The cut is placed in the
+    middle of the WIDEST gap between consecutive pooled peak values in that rank range, so the detection set is as far
+    from a threshold tie as the data allow ("tie-free inputs").  Returns (new state dict, shift, half-width of the
+    gap = decision margin)."""
+    peaks = np.sort(np.concatenate([v for v, _ in nms_peaks(center_maps)]))[::-1]
+    B = np.asarray(center_maps).shape[0]
+    lo, hi = max(1, B), min(len(peaks) - 1, int(max_per_frame * B))
+    gaps = peaks[lo - 1:hi - 1] - peaks[lo:hi]
+    j = int(np.argmax(gaps)) + lo                      # peaks[:j] fire, peaks[j:] do not
+    cut = 0.5 * (float(peaks[j - 1]) + float(peaks[j]))
+    out = dict(sd)
+    out["final_layers.2.2.bias"] = (np.asarray(sd["final_layers.2.2.bias"], np.float32) + np.float32(thresh - cut)).astype(np.float32)
+    return out, float(thresh - cut), 0.5 * float(gaps[j - lo])
+
+
 def bev_cam3dmap_anchor(fov=60, size=128):
     """get_cam3dmap_anchor, bev/model.py:77-87: 64 strictly decreasing scale anchors."""
     depth_level = np.array([1, 10, 20, 100], dtype=np.float32)

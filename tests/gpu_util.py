@@ -52,3 +52,9 @@ def conv_ref(x_nhwc_f32, w, b=None, *, stride=1, relu=False, res=None, up=1, inp
     if pow_channel >= 0:
         y[:, pow_channel] = torch.pow(1.1, y[:, pow_channel])
     return y.permute(0, 2, 3, 1).contiguous()
+
+
+def round_tf32(t):
+    """fp32 -> TF32 (10 mantissa bits, ties away from zero) like cvt.rna.tf32.f32; stays in fp32 containers."""
+    i = t.detach().cpu().float().contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)

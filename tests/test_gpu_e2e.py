@@ -35,14 +35,14 @@ def test_p1_maps_fp32_parity(params, oracle_maps):
         m.stream.synchronize()
         ec, ep = (c.cpu() - oc).abs().max().item(), (p.cpu() - op).abs().max().item()
         print(f"fp32 engine vs oracle: center {ec:.3e} params {ep:.3e}")
-        assert ec < 2e-3 and ep < 5e-3                          # ~100 fp32 layers, different summation order
+        assert ec < 2e-5 and ep < 3e-5       # ~100 fp32 layers, different summation order; measured 3.4e-6 / 5.0e-6 on B200
     # the backbone feature map itself
     nb, _ = m._net(0)                           # F32 input net
     feat = torch.zeros(2, 128, 128, 32, device="cuda")
     m.lib.b200romp_net_read_tensor(nb.net, nb.names["backbone_out"], 2, feat.data_ptr(), None)
     torch.cuda.synchronize()
     of = O.hrnet32_forward(O.to_torch_sd(params[0]), torch.from_numpy(frames).float())
-    assert (feat.cpu().permute(0, 3, 1, 2) - of).abs().max().item() < 5e-3
+    assert (feat.cpu().permute(0, 3, 1, 2) - of).abs().max().item() < 5e-5
 
 
 def test_p1_maps_bf16_tolerance(params, oracle_maps):
@@ -55,11 +55,11 @@ def test_p1_maps_bf16_tolerance(params, oracle_maps):
     print(f"bf16 engine vs fp32 oracle: center max|err| {ec:.3e} (std {oc.std():.3f}) params {ep:.3e} (std {op.std():.3f})")
     # bf16 storage of every activation through ~100 layers; SURVEY 8c measured 0.072/0.088 for a bf16-autocast
     # run of the reference itself - we must be in that regime, not better than fp32 and not broken.
-    assert ec < 0.25 * float(oc.std()) + 0.1 and ep < 0.25 * float(op.std()) + 0.3
+    assert ec < 0.08 and ep < 0.11          # 2x the values measured on B200 (0.039 / 0.054); maps have std 0.12 / 1.18
     assert np.corrcoef(c.cpu().numpy().ravel(), oc.numpy().ravel())[0, 1] > 0.995
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
 def test_p2_to_p5_planted_batch(params, precision):
     B = 4
     frames = synth.synthetic_frames(B, seed=9)
@@ -88,7 +88,9 @@ def test_p2_to_p5_planted_batch(params, precision):
     full = O.romp_forward(params[0], params[1], frames, center_override=planted)
     mp = O.mpjpe_mm(out["joints"], full["joints"])
     print(f"{precision}: persons {n}  MPJPE vs fp32 oracle {mp:.3f} mm")
-    assert mp < (0.5 if precision == "fp32" else 60.0)
+    # measured on B200: fp32 0.001 mm, tf32 0.77 mm (TF32 rounding of the conv operands, like the reference's GPU path),
+    # bf16 9.1-10.7 mm (bf16 storage of every activation); bounds = 2x measured
+    assert mp < {"fp32": 0.01, "tf32": 1.6, "bf16": 22.0}[precision]
 
 
 def test_nobody_returns_none_and_single_image_forward(params):
@@ -135,3 +137,83 @@ def test_forward_batches_pipeline_equals_forward_batch(params):
             assert np.array_equal(a[k], b[k]), k
     # batches really differ from each other (the pipeline did not return a stale slot)
     assert not np.array_equal(got[0]["smpl_thetas"], got[1]["smpl_thetas"])
+
+
+# ------------------------------------------------------------------------------------------------
+# Natural (un-planted) detections: the engines' OWN center maps decide who is detected.
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def firing(params):
+    """Weights whose center head fires on its own (synth.calibrate_center_head), the fp32 oracle's result on 4 frames, and
+    the same oracle under TF32-equivalent operand rounding = the reference's default GPU arithmetic."""
+    frames = synth.synthetic_frames(4, seed=11)
+    c, _ = O.romp_maps(params[0], frames)
+    sd, shift, margin = synth.calibrate_center_head(params[0], c.numpy())
+    ref = O.romp_forward(sd, params[1], frames)
+    ref_maps = O.romp_maps(sd, frames)
+    with O.conv_rounding("tf32"):
+        ref_tf32 = O.romp_forward(sd, params[1], frames)
+        tf32_maps = O.romp_maps(sd, frames)
+    assert ref is not None and 4 <= len(ref["cam"]) <= 40
+    return dict(sd=sd, frames=frames, margin=margin, ref=ref, ref_maps=ref_maps, ref_tf32=ref_tf32, tf32_maps=tf32_maps)
+
+
+def _det_keys(out):
+    cp = np.asarray(out["center_preds"])
+    return [(int(b), int(x), int(y)) for b, (x, y) in zip(np.asarray(out["pred_batch_ids"]), cp)]
+
+
+def test_oracle_tf32_yardstick(firing):
+    """The yardstick itself: the reference's TF32 GPU arithmetic keeps the detection set of its fp32 CPU arithmetic on
+    these inputs (the calibration margin is several times the TF32 map error) and moves the joints by well under 1 mm."""
+    ref, t = firing["ref"], firing["ref_tf32"]
+    ec = (firing["tf32_maps"][0] - firing["ref_maps"][0]).abs().max().item()
+    print(f"oracle TF32 vs fp32: center max|err| {ec:.2e}, decision margin {firing['margin']:.2e}, persons {len(ref['cam'])}")
+    assert firing["margin"] > 3 * ec
+    assert _det_keys(t) == _det_keys(ref)
+    print(f"oracle TF32 vs fp32 MPJPE {O.mpjpe_mm(t['joints'], ref['joints']):.4f} mm")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+def test_natural_detections_vs_oracle(params, firing, precision):
+    """P5 without planting: person count, (frame, x, y) of every detection and its order must equal the fp32 oracle's for
+    the fp32 and TF32 engines; MPJPE of the TF32 engine must be in the regime of the oracle's own TF32 run."""
+    f = firing
+    m = make((f["sd"], params[1]), precision, max_batch=4)
+    out = m.forward_batch(torch.from_numpy(f["frames"]))
+    assert out is not None
+    c = m.buf["center_maps"][:4].cpu()
+    ec = (c - f["ref_maps"][0]).abs()
+    e_tf = (f["tf32_maps"][0] - f["ref_maps"][0]).abs()
+    ep = (m.buf["params_maps"][:4].cpu() - f["ref_maps"][1]).abs()
+    ep_tf = (f["tf32_maps"][1] - f["ref_maps"][1]).abs()
+    got, want = _det_keys(out), _det_keys(f["ref"])
+    common = [k for k in got if k in set(want)]
+    print(f"{precision}: center map max|err| {ec.max():.2e} mean {ec.mean():.2e} (oracle-TF32: {e_tf.max():.2e} / {e_tf.mean():.2e}); "
+          f"params map {ep.max():.2e} / {ep.mean():.2e} (oracle-TF32: {ep_tf.max():.2e} / {ep_tf.mean():.2e}); "
+          f"detections {len(got)} vs oracle {len(want)}, common {len(common)}")
+    if precision in ("fp32", "tf32"):
+        assert got == want, "detection set / order differs from the fp32 oracle"
+        assert np.array_equal(out["center_preds"], f["ref"]["center_preds"].numpy())
+        mp = O.mpjpe_mm(out["joints"], f["ref"]["joints"])
+        mp_tf = O.mpjpe_mm(f["ref_tf32"]["joints"], f["ref"]["joints"])
+        print(f"{precision}: MPJPE vs fp32 oracle {mp:.4f} mm (oracle-TF32 vs oracle-fp32: {mp_tf:.4f} mm)")
+        if precision == "fp32":
+            assert mp < 0.01 and ec.max() < 2e-5
+        else:
+            # Same arithmetic as the oracle's TF32 run up to summation order and BN folding before/after rounding: the
+            # two are independent realisations of one error distribution.  Over the 2 x 10^6 map values the means
+            # agree within a few % (measured on B200: center 4.82e-4 vs 4.85e-4); the MPJPE is an average over only
+            # 8 persons x 24 joints and scatters more (measured 0.91 vs 0.65 mm) - bounded by 2x the yardstick.
+            assert ec.mean() <= 1.25 * e_tf.mean() + 1e-5 and ec.max() <= 1.5 * e_tf.max()
+            assert ep.mean() <= 1.25 * ep_tf.mean() + 1e-5 and ep.max() <= 2.0 * ep_tf.max()
+            assert mp <= 2.0 * mp_tf + 0.01
+    else:
+        # bf16 engine: 8-bit mantissa storage of every activation - detections may flip near the threshold; what it
+        # keeps must be the oracle's, and most of the oracle's must be found
+        assert len(common) >= 0.75 * len(want) and len(got) <= 1.25 * len(want) + 1
+        idx_g = [got.index(k) for k in common]
+        idx_w = [want.index(k) for k in common]
+        mp = O.mpjpe_mm(out["joints"][idx_g], f["ref"]["joints"].numpy()[idx_w])
+        print(f"bf16: MPJPE on the {len(common)} common detections {mp:.2f} mm")
+        assert mp < 25.0
