@@ -218,6 +218,15 @@ int b200romp_gather_rows(const void* src, int row_bytes, const int* sel, const i
                          b200romp_stream stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Row a1/f2: `img_preprocess(image)` (simple_romp/romp/utils.py:16-30, called from ROMP.forward main.py:161): BGR->RGB,
+ * centre zero-pad to a square (padding_image :16-24), cv2.resize(INTER_CUBIC) to out_size x out_size, uint8 - one kernel
+ * from the raw BGR image in device memory to the network's input frame.  Bit-exact with OpenCV's own 8-bit bicubic
+ * resize (resize.cpp; not with the closed-source IPP fast path some OpenCV builds dispatch to, which differs by +-1 LSB).
+ * pad_info6 (HOST, may be NULL) receives [top, bottom, left, right, h, w] like padding_image. */
+int b200romp_preprocess_bgr(const unsigned char* img_bgr_device, int h, int w, int row_stride_bytes, int out_size,
+                            unsigned char* out_rgb_device, float* pad_info6_host, b200romp_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Frame-sharded multi-GPU collection (the reference's DataParallel bookkeeping it stands in for:
  * romp/lib/maps_utils/result_parser.py:59-64,123-124).  Packs the per-person output arrays of one rank into the
  * fixed-width record buffer that a single NCCL all-gather ships:

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "lib", "libb200romp.so")
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["net.cu", "conv_simt.cu", "conv_tc.cu", "conv_tc_s2.cu", "conv_stem_tc.cu", "conv_tc_2cta.cu", "parse.cu", "smpl.cu", "project.cu", "bev.cu", "pack.cu"]
+SOURCES = ["net.cu", "conv_simt.cu", "conv_tc.cu", "conv_tc_s2.cu", "conv_stem_tc.cu", "conv_tc_2cta.cu", "parse.cu", "smpl.cu", "project.cu", "bev.cu", "pack.cu", "preproc.cu"]
 
 F32, BF16, U8 = 0, 1, 2
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, ENGINE_TF32 = 0, 1, 2, 3
@@ -151,6 +151,7 @@ def load():
     _sig(lib.b200romp_bev_regress, i32, vp, vp, vp, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp)
     _sig(lib.b200romp_bev_post, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, fp, f32, f32, f32, vp, vp, vp, vp, vp)
     _sig(lib.b200romp_gather_rows, i32, vp, i32, vp, vp, i32, vp, vp)
+    _sig(lib.b200romp_preprocess_bgr, i32, vp, i32, i32, i32, i32, vp, fp, vp)
     _sig(lib.b200romp_pack_rows, i32, C.POINTER(vp), ip, i32, vp, i32, i32, i32, i32, vp, i32, vp)
     if lib.b200romp_version() != 100:
         raise RuntimeError("libb200romp.so version mismatch - rebuild")
@@ -176,5 +177,5 @@ EXPORTS = [
     "b200romp_smpl_workspace_floats", "b200romp_smpl_forward", "b200romp_project",
     "b200romp_bev_create", "b200romp_bev_destroy", "b200romp_bev_bv_input", "b200romp_bev_center3d",
     "b200romp_bev_parse_workspace_bytes", "b200romp_bev_parse3d", "b200romp_bev_regress", "b200romp_bev_post",
-    "b200romp_gather_rows", "b200romp_pack_rows",
+    "b200romp_gather_rows", "b200romp_pack_rows", "b200romp_preprocess_bgr",
 ]

@@ -56,6 +56,9 @@ def romp_settings(input_args=sys.argv[1:]):
                         help="conv arithmetic: bf16 tensor cores (fast), tf32 tensor cores on fp32 tensors (the reference's "
                              "default GPU arithmetic, cudnn.allow_tf32) or fp32 CUDA cores (strict parity)")
     parser.add_argument("--max_batch", type=int, default=64, help="largest batch forward_batch will be given")
+    parser.add_argument("--cam_trans", type=str, default="lsq", choices=["lsq", "pnp"],
+                        help="cam_trans estimator: lsq = closed-form least squares on the GPU (the reference's fallback, "
+                             "utils.py:347-389); pnp = the reference's default cv2.solvePnPRansac per person on the host")
     args = parser.parse_args(input_args)
     if not os.path.exists(args.smpl_path):
         alt = args.smpl_path.replace("SMPL_NEUTRAL.pth", "smpl_packed_info.pth")   # main.py:50-52
@@ -75,11 +78,57 @@ def padding_image(image):
 
 
 def img_preprocess(image, input_size=512):
-    """utils.py:26-30 (host side, OpenCV): BGR->RGB, square zero pad, cubic resize; returns uint8 [1,512,512,3]."""
+    """utils.py:26-30 restated on the host with OpenCV exactly like the reference (BGR->RGB, square zero pad, cubic resize;
+    returns uint8 [1,512,512,3]).  ``ROMP.forward`` does NOT use it - it runs ``ROMP.preprocess`` (one CUDA kernel); this
+    host mirror exists for tests and for callers that batch pre-sized frames themselves."""
     import cv2
     image = cv2.cvtColor(image, cv2.COLOR_BGR2RGB)
     pad, info = padding_image(image)
     return cv2.resize(pad, (input_size, input_size), interpolation=cv2.INTER_CUBIC)[None], info
+
+
+INVALID_TRANS = np.array([-1.0, -1.0, -1.0], np.float32)      # utils.py:295
+
+
+def _translation_lsq_host(S, p2, focal, center):
+    """estimate_translation_np (utils.py:347-389, the reference's own fallback), all joints valid, fp64 on the host."""
+    n = S.shape[0]
+    Z = np.reshape(np.tile(S[:, 2], (2, 1)).T, -1)
+    XY = np.reshape(S[:, :2], -1)
+    O_ = np.tile(center, n)
+    Fv = np.tile(np.array([focal, focal], np.float64), n)
+    w = np.ones(2 * n)
+    Q = np.array([Fv * np.tile(np.array([1, 0]), n), Fv * np.tile(np.array([0, 1]), n), O_ - np.reshape(p2, -1)]).T
+    c = (np.reshape(p2, -1) - O_) * Z - Fv * XY
+    W = np.diagflat(w)
+    Q, c = W @ Q, W @ c
+    return np.linalg.solve(Q.T @ Q, Q.T @ c)
+
+
+def estimate_translation_pnp(joints, cam, focal_length=443.4, img_size=512.0):
+    """``--cam_trans pnp``: the reference's DEFAULT cam_trans (convert_cam_to_3d_trans2 post_parser.py:96-101 ->
+    estimate_translation utils.py:391-436 -> estimate_translation_cv2 :331-345): per person
+    cv2.solvePnPRansac(EPnP, reprojectionError 20, 100 iterations) on the 24 SMPL joints against their weak-perspective
+    projection (pj2d + 1) * 256, K = diag(443.4) with principal point 256; INVALID_TRANS when RANSAC finds no inliers,
+    the closed-form least squares (:347-389) when OpenCV raises.  Host side (OpenCV), like the reference; the device
+    default (``--cam_trans lsq``) is that closed form for every person (b200romp_project)."""
+    import cv2
+    joints, cam = np.asarray(joints, np.float32), np.asarray(cam, np.float32)
+    j3 = np.ascontiguousarray(joints[:, :24])
+    p2 = (j3[:, :, :2] * cam[:, None, 0:1] + cam[:, None, 1:3] + 1.0) * (img_size / 2.0)      # batch_orth_proj utils.py:309-315
+    K = np.eye(3)
+    K[0, 0] = K[1, 1] = focal_length
+    K[:2, 2] = img_size // 2
+    out = np.zeros((len(j3), 3), np.float32)
+    for i in range(len(j3)):
+        try:
+            _, _, tvec, inliers = cv2.solvePnPRansac(j3[i], p2[i].astype(np.float32), K, None, flags=cv2.SOLVEPNP_EPNP,
+                                                     reprojectionError=20, iterationsCount=100)
+            out[i] = INVALID_TRANS if inliers is None else tvec[:, 0]
+        except Exception:
+            out[i] = _translation_lsq_host(j3[i].astype(np.float64), p2[i].astype(np.float64), focal_length,
+                                           np.array([img_size / 2.0, img_size / 2.0]))
+    return out
 
 
 def _ptr(t):
@@ -121,6 +170,25 @@ class SMPLParser:
             pass
 
 
+class MapsModule(torch.nn.Module):
+    """``ROMP.model``: seam S1 as a module, like the reference's ``self.model`` (ROMPv1 wrapped in nn.DataParallel,
+    main.py:74-77): ``model(frames)`` with frames [B,512,512,3] (uint8 / float32 0..255, device) returns
+    ``(center_maps [B,1,64,64], params_maps [B,145,64,64])``.  Difference to the reference, by design: the cam-scale
+    ``1.1**x`` of main.py:113 is already applied to ``params_maps[:,0]`` (it is fused into the head conv's epilogue)."""
+
+    def __init__(self, owner):
+        super().__init__()
+        object.__setattr__(self, "_owner", owner)       # not a sub-module: no parameter / state-dict recursion
+
+    def forward(self, frames):
+        o = self._owner
+        o._after_producers(frames)
+        with torch.cuda.stream(o.stream):
+            c, p = o.run_maps(frames.contiguous())
+        torch.cuda.current_stream(o.tdevice).wait_stream(o.stream)
+        return c, p
+
+
 class ROMP(torch.nn.Module):
     """``ROMP(settings)(image_bgr)`` - same contract as simple_romp/romp/main.py:64-176."""
 
@@ -149,6 +217,7 @@ class ROMP(torch.nn.Module):
                 smpl_pack = torch.load(s.smpl_path, map_location="cpu")        # smpl.py:41
             self.smpl = SMPLParser(smpl_pack, self.device_index)
         self._alloc(self.max_batch)
+        self.model = MapsModule(self)
 
     # ------------------------------------------------------------------------------------------
     def _net(self, in_dtype):
@@ -181,6 +250,7 @@ class ROMP(torch.nn.Module):
             self.slots.append(dict(dev=d, host=None, count_host=torch.zeros(1, dtype=torch.int32).pin_memory(),
                                    done=torch.cuda.Event(), frames={}, h2d=torch.cuda.Event()))
         self._slot = 0
+        self._raw_host = self._raw_dev = None
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.d2h_stream = torch.cuda.Stream(device=dev)
 
@@ -318,15 +388,21 @@ class ROMP(torch.nn.Module):
         out = self.collect(to_numpy)
         if out is not None and to_numpy and own:
             out = {k: np.array(v) for k, v in out.items()}
+            if getattr(self.settings, "cam_trans", "lsq") == "pnp" and self.calc_smpl:
+                out["cam_trans"] = estimate_translation_pnp(out["joints"], out["cam"])
         return out
 
     @torch.no_grad()
-    def forward_batches(self, batches, offsets=None, center_override=None, to_numpy=True):
+    def forward_batches(self, batches, offsets=None, center_override=None, to_numpy=True, gather=None, frame_offset=0):
         """Pipelined streaming over an iterable of host frame batches (video): yields one result dict (or None) per
         batch, in order.  H2D of batch i+1 (copy stream) and D2H of batch i-1 (read-back stream) overlap the
         kernels of batch i; the host waits only for the H2D copy of the batch it just handed over (so a caller may
         refill one pinned buffer in a decode loop) and for the person count of an already finished batch.  With
-        ``to_numpy=True`` the yielded arrays are views of pinned mirrors, valid until the second-next batch is yielded."""
+        ``to_numpy=True`` the yielded arrays are views of pinned mirrors, valid until the second-next batch is yielded.
+        Sharded (multi-GPU) use: pass ``gather`` (a shard.ShardGather built on ``record_layout()``) and this rank's
+        ``frame_offset``; each batch's records are then packed and all-gathered on the gather's side stream right after
+        its kernels, and the generator yields ``(own_result, gather_handle)`` pairs (own shard read back to this rank's
+        host; ``gather.result(handle)`` gives every rank's persons on the device)."""
         off = offsets if offsets is not None else [0, 512, 0, 512, 512, 512]
         pending = None
         self._after_producers(center_override)
@@ -346,31 +422,78 @@ class ROMP(torch.nn.Module):
                 slot["h2d"].record(self.copy_stream)
             with torch.cuda.stream(self.stream):
                 self.stream.wait_event(slot["h2d"])
+                if slot.get("packed") is not None:
+                    self.stream.wait_event(slot["packed"])          # the gather's pack kernel has read the slot's previous results
                 self.run_maps(fd)
                 self.run_post(B, off, center_override, slot)
                 slot["done"].record(self.stream)
+                if gather is not None:
+                    fields, count = self.record_fields(slot)
+                    slot["gather"] = gather.submit(fields, count, frame_offset)
+                    slot["packed"] = slot["gather"]["packed"]
             if not frames.is_cuda:
                 slot["h2d"].synchronize()     # the caller may refill its (single) host buffer as soon as we yield / pull the next batch
             if pending is not None:
-                yield self._read_back(pending, to_numpy)
+                res = self._read_back(pending, to_numpy)
+                yield (res, pending["gather"]) if gather is not None else res
             pending = slot
         if pending is not None:
-            yield self._read_back(pending, to_numpy)
+            res = self._read_back(pending, to_numpy)
+            yield (res, pending["gather"]) if gather is not None else res
 
     def _read_back(self, slot, to_numpy=True):
         self.d2h_stream.wait_event(slot["done"])
         return self.collect(to_numpy, slot, self.d2h_stream)   # device views stay valid until the slot's next batch
 
     @torch.no_grad()
+    def preprocess(self, image, out=None):
+        """img_preprocess (utils.py:26-30) on the GPU: raw HxWx3 uint8 BGR image (numpy / host tensor / device tensor) ->
+        ``out`` [512,512,3] uint8 RGB on the device (allocated when None) + pad info [top,bottom,left,right,h,w].
+        One kernel (b200romp_preprocess_bgr) on self.stream; the only host work is the H2D copy of the raw image."""
+        img = torch.from_numpy(np.ascontiguousarray(image)) if isinstance(image, np.ndarray) else image
+        assert img.dtype == torch.uint8 and img.dim() == 3 and img.shape[2] == 3, "image must be HxWx3 uint8 (BGR)"
+        h, w = int(img.shape[0]), int(img.shape[1])
+        if out is None:
+            out = torch.empty((512, 512, 3), dtype=torch.uint8, device=self.tdevice)
+        if img.is_cuda:
+            self._after_producers(img)
+            raw = img.contiguous()
+        else:
+            n = img.numel()
+            if self._raw_host is None or self._raw_host.numel() < n:
+                self._raw_host = torch.empty(max(n, 1 << 22), dtype=torch.uint8).pin_memory()
+                self._raw_dev = torch.empty(self._raw_host.numel(), dtype=torch.uint8, device=self.tdevice)
+            self.stream.synchronize()                       # the previous image's H2D has left the pinned staging buffer
+            self._raw_host[:n].copy_(img.reshape(-1))
+            raw = self._raw_dev[:n]
+            with torch.cuda.stream(self.stream):
+                raw.copy_(self._raw_host[:n], non_blocking=True)
+        pad = (C.c_float * 6)()
+        _lib.check(self.lib.b200romp_preprocess_bgr(_ptr(raw), h, w, 3 * w, 512, _ptr(out), pad,
+                                                    C.c_void_p(self.stream.cuda_stream)), "preprocess_bgr")
+        return out, np.array(list(pad), dtype=np.float32)
+
+    @torch.no_grad()
     def forward(self, image, signal_ID=0, **kwargs):
-        """image: HxWx3 uint8 BGR (cv2.imread).  main.py:160-176."""
-        input_image, pad_info = img_preprocess(image)
-        out = self.forward_batch(torch.from_numpy(input_image), offsets=pad_info)
+        """image: HxWx3 uint8 BGR (cv2.imread).  main.py:160-176; preprocessing, model, parse, SMPL and projection all run
+        on the GPU - OpenCV is not involved."""
+        self._slot ^= 1
+        slot = self.slots[self._slot]
+        fd = self._staging(slot, torch.uint8, 1)
+        _, pad_info = self.preprocess(image, out=fd[0])
+        with torch.cuda.stream(self.stream):
+            self.run_maps(fd)
+            self.run_post(1, pad_info)
+            slot["done"].record(self.stream)
+        out = self.collect(True)
         if out is None:
             print("None person detected")                                       # post_parser.py:139
             return None
         out.pop("pred_batch_ids")
-        return out                                                               # arrays own their memory like the reference's
+        out = {k: np.array(v) for k, v in out.items()}                           # arrays own their memory like the reference's
+        if getattr(self.settings, "cam_trans", "lsq") == "pnp" and self.calc_smpl:
+            out["cam_trans"] = estimate_translation_pnp(out["joints"], out["cam"])
+        return out
 
 
 default_settings = None   # the reference evaluates romp_settings([]) at import (main.py:62); we do not

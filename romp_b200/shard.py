@@ -167,6 +167,8 @@ class ShardGather:
             with torch.cuda.stream(self.stream):
                 self.stream.wait_event(ready)
                 pack_rows(self.layout, fields, count, frame_offset, self.send[slot], self.stream.cuda_stream)
+                packed = torch.cuda.Event()
+                packed.record(self.stream)          # from here on the caller may overwrite `fields`
                 recv = self._gather(slot, rows)
                 done = torch.cuda.Event()
                 done.record(self.stream)
@@ -175,8 +177,8 @@ class ShardGather:
                     t.record_stream(self.stream)
         else:
             pack_rows(self.layout, fields, count, frame_offset, self.send[slot])
-            recv, done = self._gather(slot, rows), None
-        return dict(slot=slot, rows=rows, recv=recv, done=done)
+            recv, done, packed = self._gather(slot, rows), None, None
+        return dict(slot=slot, rows=rows, recv=recv, done=done, packed=packed)
 
     def wait(self, handle, stream=None):
         """Make `stream` (default: the current stream) wait for the gather of `handle` - device-side join, no host sync."""

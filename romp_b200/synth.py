@@ -237,6 +237,30 @@ def plant_centers(batch: int, seed: int = 0, kmin: int = 1, kmax: int = 10, size
 # --------------------------------------------------------------------------------------
 # BEV head parameters (simple_romp/bev/model.py:104-187): enumeration + synthetic values
 # --------------------------------------------------------------------------------------
+def plant_centers_3d(batch: int, seed: int = 0, kmin: int = 1, kmax: int = 10, z_lo: int = 24, z_hi: int = 44, min_sep: int = 20):
+    """BEV cfg3 workload: 3-D center maps [B,64,128,128] (low uniform background + K_b ~ U{kmin..kmax} planted peaks per
+    frame) whose persons SURVIVE BEV's per-frame post-filters, so that the step really processes <= 10 kept persons
+    per frame: depth levels z_lo..z_hi (scale anchors 1.08..0.45: `remove_outlier` only drops scales < 0.25,
+    bev/post_parser.py:200-222) and >= min_sep cells (= 4*min_sep pixels) apart in the image plane, far beyond the
+    duplicate-suppression radius nms_thresh * 512/640 * 2*scale pixels (bev/post_parser.py:167-198).
+    Returns (volume float32, number of planted persons)."""
+    rs = np.random.RandomState(seed + 32452843)
+    vol = rs.uniform(0, 0.05, size=(batch, 64, 128, 128)).astype(np.float32)
+    persons = 0
+    for b in range(batch):
+        k = rs.randint(kmin, kmax + 1)
+        cells, tries = [], 0
+        while len(cells) < k and tries < 20000:
+            tries += 1
+            y, x = rs.randint(8, 120), rs.randint(8, 120)
+            if all(max(abs(y - cy), abs(x - cx)) >= min_sep for cy, cx in cells):
+                cells.append((y, x))
+        for (y, x) in cells:
+            vol[b, rs.randint(z_lo, z_hi + 1), y, x] = rs.uniform(0.3, 1.0)
+            persons += 1
+    return vol, persons
+
+
 def nms_peaks(center_maps):
     """Values and flat indices of the 5x5 local maxima of [B,1,S,S] maps (CenterMap.nms, post_parser.py:50-54), per frame."""
     cm = np.asarray(center_maps, np.float32)[:, 0]

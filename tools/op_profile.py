@@ -19,12 +19,13 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--top", type=int, default=400)
+    ap.add_argument("--precision", type=str, default="bf16", choices=["bf16", "tf32", "fp32"])
     args = ap.parse_args()
     from romp_b200 import graph, synth, _lib
 
     torch.cuda.set_device(0)
     B = args.batch
-    nb, io = graph.build_romp(synth.romp_state_dict(0), 0, "bf16", _lib.U8, max_batch=B)
+    nb, io = graph.build_romp(synth.romp_state_dict(0), 0, args.precision, _lib.U8, max_batch=B)
     lib = nb.lib
     frames = torch.randint(0, 256, (B, 512, 512, 3), dtype=torch.uint8, device="cuda")
     ext = {}
