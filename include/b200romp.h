@@ -91,6 +91,10 @@ typedef struct b200romp_sum_desc {
 } b200romp_sum_desc;
 /* Returns op id (ops run in the order they were added, convs and sums alike). */
 int b200romp_net_add_sum(b200romp_net* net, const b200romp_sum_desc* desc);
+/* Concurrency lane (0..3) of an op inside the captured CUDA graph: ops of different lanes that do not depend on each other
+ * through a tensor (or a recycled workspace buffer) may overlap - the parallel branches of a HighResolutionModule
+ * (model.py:226-233) and the three ROMP heads (model.py:475-478).  Default lane 0.  Call before finalize. */
+int b200romp_net_set_lane(b200romp_net* net, int op, int lane);
 /* Packs weights for the chosen engines, uploads them, plans buffer reuse and allocates the workspace. */
 int b200romp_net_finalize(b200romp_net* net, int max_batch);
 int b200romp_net_bind(b200romp_net* net, int tensor, void* device_ptr);
@@ -225,6 +229,22 @@ int b200romp_gather_rows(const void* src, int row_bytes, const int* sel, const i
  * pad_info6 (HOST, may be NULL) receives [top, bottom, left, right, h, w] like padding_image. */
 int b200romp_preprocess_bgr(const unsigned char* img_bgr_device, int h, int w, int row_stride_bytes, int out_size,
                             unsigned char* out_rgb_device, float* pad_info6_host, b200romp_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Row f4: the temporal stage of ROMP.forward with --temporal_optimize (main.py:117-157): One-Euro smoothing of
+ * (smpl_thetas, smpl_betas, cam) per tracked person, between seams S2 and S3.  Restates LowPassFilter / OneEuroFilter /
+ * create_OneEuroFilter / smooth_results / smooth_global_rot_matrix (utils.py:188-192,203-270) in fp32 on the device; the
+ * filter state of every track lives in device memory inside the handle.  slot[i] (device int32) = state slot of person i
+ * (0 <= slot < max_tracks; a slot whose state was reset initialises on its next sample) or -1 = leave person i untouched.
+ * thetas [n,72], betas [n,betas_stride] (first n_betas smoothed), cam [n,3] are updated IN PLACE; the person count is
+ * min(n, *d_count) when d_count != NULL.  The track association (norfair in the reference) is the caller's. */
+typedef struct b200romp_tracks b200romp_tracks;
+b200romp_tracks* b200romp_tracks_create(int device, int max_tracks);
+void b200romp_tracks_destroy(b200romp_tracks* tracks);
+/* forget the state of one slot (slot >= 0) or of all slots (slot = -1) */
+int b200romp_tracks_reset(b200romp_tracks* tracks, int slot, b200romp_stream stream);
+int b200romp_one_euro_smooth(b200romp_tracks* tracks, const int* slot, int n, const int* d_count, float* thetas, float* betas,
+                             int betas_stride, int n_betas, float* cam, float smooth_coeff, float freq, b200romp_stream stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Frame-sharded multi-GPU collection (the reference's DataParallel bookkeeping it stands in for:

@@ -276,6 +276,11 @@ def quat_to_aa(q):
     return aa
 
 
+def rotmat_to_aa(Rm):
+    """rotation_matrix_to_angle_axis, utils.py:535-552: [N,3,3] -> [N,3]."""
+    return quat_to_aa(rotmat_to_quat(Rm))
+
+
 def rot6d_to_aa(x6):
     """rot6D_to_angular, utils.py:471-475: [N, J*6] -> [N, J*3]."""
     n = x6.shape[0]

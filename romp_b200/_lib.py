@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "lib", "libb200romp.so")
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["net.cu", "conv_simt.cu", "conv_tc.cu", "conv_tc_s2.cu", "conv_stem_tc.cu", "conv_tc_2cta.cu", "parse.cu", "smpl.cu", "project.cu", "bev.cu", "pack.cu", "preproc.cu"]
+SOURCES = ["net.cu", "conv_simt.cu", "conv_tc.cu", "conv_tc_s2.cu", "conv_stem_tc.cu", "conv_tc_2cta.cu", "parse.cu", "smpl.cu", "project.cu", "bev.cu", "pack.cu", "preproc.cu", "temporal.cu"]
 
 F32, BF16, U8 = 0, 1, 2
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, ENGINE_TF32 = 0, 1, 2, 3
@@ -126,6 +126,7 @@ def load():
     _sig(lib.b200romp_net_add_const_tensor, i32, vp, i32, i32, i32, i32, vp)
     _sig(lib.b200romp_net_add_conv, i32, vp, C.POINTER(ConvDesc), fp, fp)
     _sig(lib.b200romp_net_add_sum, i32, vp, C.POINTER(SumDesc))
+    _sig(lib.b200romp_net_set_lane, i32, vp, i32, i32)
     _sig(lib.b200romp_net_finalize, i32, vp, i32)
     _sig(lib.b200romp_net_bind, i32, vp, i32, vp)
     _sig(lib.b200romp_net_run, i32, vp, i32, vp)
@@ -151,6 +152,10 @@ def load():
     _sig(lib.b200romp_bev_regress, i32, vp, vp, vp, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp)
     _sig(lib.b200romp_bev_post, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, fp, f32, f32, f32, vp, vp, vp, vp, vp)
     _sig(lib.b200romp_gather_rows, i32, vp, i32, vp, vp, i32, vp, vp)
+    _sig(lib.b200romp_tracks_create, vp, i32, i32)
+    _sig(lib.b200romp_tracks_destroy, None, vp)
+    _sig(lib.b200romp_tracks_reset, i32, vp, i32, vp)
+    _sig(lib.b200romp_one_euro_smooth, i32, vp, vp, i32, vp, vp, vp, i32, i32, vp, f32, f32, vp)
     _sig(lib.b200romp_preprocess_bgr, i32, vp, i32, i32, i32, i32, vp, fp, vp)
     _sig(lib.b200romp_pack_rows, i32, C.POINTER(vp), ip, i32, vp, i32, i32, i32, i32, vp, i32, vp)
     if lib.b200romp_version() != 100:
@@ -169,7 +174,7 @@ def check(rc, what=""):
 EXPORTS = [
     "b200romp_version", "b200romp_last_error", "b200romp_device_info", "b200romp_net_create",
     "b200romp_net_destroy", "b200romp_net_add_tensor", "b200romp_net_add_const_tensor", "b200romp_net_add_conv",
-    "b200romp_net_add_sum",
+    "b200romp_net_add_sum", "b200romp_net_set_lane",
     "b200romp_net_finalize", "b200romp_net_bind", "b200romp_net_run", "b200romp_net_read_tensor",
     "b200romp_net_describe", "b200romp_net_num_launches", "b200romp_net_workspace_bytes", "b200romp_net_profile",
     "b200romp_conv2d",
@@ -177,5 +182,6 @@ EXPORTS = [
     "b200romp_smpl_workspace_floats", "b200romp_smpl_forward", "b200romp_project",
     "b200romp_bev_create", "b200romp_bev_destroy", "b200romp_bev_bv_input", "b200romp_bev_center3d",
     "b200romp_bev_parse_workspace_bytes", "b200romp_bev_parse3d", "b200romp_bev_regress", "b200romp_bev_post",
-    "b200romp_gather_rows", "b200romp_pack_rows", "b200romp_preprocess_bgr",
+    "b200romp_gather_rows", "b200romp_pack_rows", "b200romp_preprocess_bgr", "b200romp_tracks_create", "b200romp_tracks_destroy",
+    "b200romp_tracks_reset", "b200romp_one_euro_smooth",
 ]

@@ -11,6 +11,9 @@
 namespace b200romp {
 
 void set_error(const char* fmt, ...);
+// -1 = default; 0 = launch the next tcgen05 convs without the programmatic-dependent-launch attribute (net.cu: ops that wait
+// for another lane inside the captured graph).  Defined in conv_tc.cu.
+extern thread_local int g_tc_pdl_override;
 
 #define B2R_CUDA_OK(expr)                                                                         \
   do {                                                                                            \

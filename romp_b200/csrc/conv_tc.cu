@@ -32,6 +32,8 @@
 
 namespace b200romp {
 
+thread_local int g_tc_pdl_override = -1;
+
 template <int KS, int CIN, int NT, bool PER_TAP, int KSPLIT, int EB>
 struct TcCfg {
   static constexpr int TAPS = KS * KS;
@@ -67,7 +69,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   uint8_t* sB = smem;
   uint8_t* sA = smem + Cfg::B_BYTES;
   uint8_t* epi_smem = sA + (size_t)stages * Cfg::STAGE_BYTES;       // TMA-epilogue staging tiles (1024 B aligned), if any
-  uint64_t* full = reinterpret_cast<uint64_t*>(epi_smem + tc_epi_total_bytes(tma_epi, NT));
+  uint64_t* full = reinterpret_cast<uint64_t*>(epi_smem + (EB == 4 ? tc_epi_f32_total_bytes(tma_epi) : tc_epi_total_bytes(tma_epi, NT)));
   uint64_t* empty = full + stages;
   uint64_t* b_full = empty + stages;
   uint64_t* tmem_full = b_full + 1;
@@ -202,6 +204,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       }
       if (nrings == 2) { const int ts = stage; stage = stage_other; stage_other = ts; const uint32_t tp = phase; phase = phase_other; phase_other = tp; }
     }
+  } else if (EB == 4 && tma_epi) {
+    tc_epilogue_loop_tma_f32<NT>(p, epi_maps, tma_epi, epi_smem, res_bar, tmem_base, tmem_full, tmem_empty, s_bias, tiles_x, per_frame,
+                                 num_tiles);
   } else if (EB == 2 && KSPLIT == 1 && NT == 32 && (tma_epi & kEpiCoalesced)) {   // (instantiated for NT = 32 only: register pressure)
     tc_epilogue_loop_coalesced<NT>(p, tma_epi, epi_smem, tmem_base, tmem_full, tmem_empty, s_bias, tiles_x, per_frame, num_tiles);
   } else if (EB == 2 && KSPLIT == 1 && tma_epi) {
@@ -363,6 +368,52 @@ int tc_epi_prepare(const ConvParams& p, int nt, bool ptrs_final, TcConvPlan* pla
   return plan->tma_epi;
 }
 
+int tc_epi_prepare_f32(const ConvParams& p, int nt, bool ptrs_final, int avail, int stage_bytes, TcConvPlan* plan) {
+  plan->tma_epi = 0;
+  const char* e = getenv("B200ROMP_TC_NO_TMA_EPI");
+  if (e && e[0] == '1') return 0;
+  if (!ptrs_final || p.out_dtype != B200ROMP_F32 || p.out_nchw || p.up != 1 || p.pow_channel >= 0) return 0;
+  if (p.cout % nt != 0 || nt % 32 != 0 || (reinterpret_cast<uintptr_t>(p.out) & 15) != 0 || (p.out_C % 4) != 0 || (p.out_c_off % 4) != 0) return 0;
+  const bool res_tma = p.res != nullptr;
+  if (res_tma && (p.res_dtype != B200ROMP_F32 || p.res_broadcast || (reinterpret_cast<uintptr_t>(p.res) & 15) != 0 || (p.res_C % 4) != 0 ||
+                  (p.res_c_off % 4) != 0))
+    return 0;
+  PFN_encodeTiled encode = tc_get_encode();
+  if (!encode) return 0;
+  auto make = [&](const void* base, int C, unsigned char* dst) -> bool {
+    const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)p.Wout, (cuuint64_t)p.Hout, (cuuint64_t)p.B};
+    const cuuint64_t gstr[3] = {(cuuint64_t)C * 4, (cuuint64_t)p.Wout * C * 4, (cuuint64_t)p.Hout * p.Wout * C * 4};
+    const cuuint32_t box[4] = {32, 8, 4, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUtensorMap tm;
+    if (encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return false;
+    memcpy(dst, &tm, sizeof(tm));
+    return true;
+  };
+  if (!make(p.out, p.out_C, plan->tmap_epi[0])) return 0;
+  if (res_tma) {
+    if (!make(p.res, p.res_C, plan->tmap_epi[1])) return 0;
+  } else {
+    memcpy(plan->tmap_epi[1], plan->tmap_epi[0], 128);
+  }
+  const int flags = kTmaEpiOut | (res_tma ? kTmaEpiRes : 0);
+  // staging depth: 3 buffers with a residual (compute / prefetch / store in flight), 2 without, while >= 4 pipeline stages
+  // remain, else 2 buffers; a plan that cannot keep 4 stages next to two buffers per warp uses the direct epilogue (measured:
+  // 256->256 @16x16 with one buffer and 3 stages 118 us against 88 us for the direct epilogue with 6 stages)
+  const int want = res_tma ? 3 : 2;
+  for (int min_stages = 4; min_stages >= 4; --min_stages)
+    for (int nb = want; nb >= 2; --nb) {
+      const int bytes = kEpiWarps * nb * kF32ChunkBytes;
+      if ((avail - bytes) / stage_bytes >= min_stages) {
+        plan->tma_epi = tc_epi_with_nbuf(flags, nb);
+        return bytes;
+      }
+    }
+  return 0;
+}
+
 int tc_conv_prepare(const ConvParams& p, int ksize, int stride, const float* w_oihw, int sm_count, bool ptrs_final, TcConvPlan* plan,
                     std::vector<void*>* allocs) {
   if (stride == 2) return tc_s2_prepare(p, w_oihw, sm_count, ptrs_final, plan, allocs);
@@ -402,6 +453,8 @@ int tc_conv_prepare(const ConvParams& p, int ksize, int stride, const float* w_o
       plan->tma_epi = tc_epi_with_nbuf(plan->tma_epi, nb) | (tc_epi_want_coalesced(nt) ? kEpiCoalesced : 0);
       epi_bytes = tc_epi_total_bytes(plan->tma_epi, nt);
     }
+  } else if (eb == 4) {
+    epi_bytes = tc_epi_prepare_f32(p, nt, ptrs_final, budget - bbytes(nt), stage_bytes, plan);
   }
   int stages = (budget - bbytes(nt) - epi_bytes) / stage_bytes;
   stages = std::min(stages, per_tap ? 12 : 8);   // split into two rings (one per MMA warp)

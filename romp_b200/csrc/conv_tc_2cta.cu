@@ -51,7 +51,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   uint8_t* sB = smem;
   uint8_t* sA = smem + (Cfg::B_BYTES + 1023) / 1024 * 1024;
   uint8_t* epi_smem = sA + (size_t)stages * Cfg::STAGE_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(epi_smem + tc_epi_total_bytes(tma_epi, NT));
+  uint64_t* full = reinterpret_cast<uint64_t*>(epi_smem + (EB == 4 ? tc_epi_f32_total_bytes(tma_epi) : tc_epi_total_bytes(tma_epi, NT)));
   uint64_t* empty = full + stages;
   uint64_t* b_full = empty + stages;
   uint64_t* b_peer = b_full + 1;
@@ -189,6 +189,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       }
       if (nrings == 2) { const int ts = stage; stage = stage_other; stage_other = ts; const uint32_t tp = phase; phase = phase_other; phase_other = tp; }
     }
+  } else if (EB == 4 && tma_epi) {
+    tc_epilogue_loop_tma_f32<NT, true>(p, epi_maps, tma_epi, epi_smem, res_bar, tmem_base, tmem_full, tmem_empty, s_bias, tiles_x,
+                                       per_frame, num_tiles);
   } else if (EB == 4 || tma_epi == 0) {
     tc_epilogue_loop<NT, 1, true>(p, tmem_base, tmem_full, tmem_empty, s_bias, tiles_x, per_frame, num_tiles);
   } else {
@@ -256,7 +259,8 @@ static int tc2_inst(const TcConvPlan& plan, const ConvParams& p, cudaStream_t st
   const int tiles_x = p.Wout / 8, tiles_y = p.Hout / 16;
   const int num_tiles = tiles_x * tiles_y * p.B;
   dim3 grid(std::min(plan.grid_x, num_tiles) & ~1, plan.grid_y);
-  static const bool pdl = [] { const char* e = getenv("B200ROMP_NO_PDL"); return !(e && e[0] == '1'); }();
+  static const bool pdl_default = [] { const char* e = getenv("B200ROMP_NO_PDL"); return !(e && e[0] == '1'); }();
+  const bool pdl = pdl_default && g_tc_pdl_override != 0;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(tc_threads(EB));
@@ -313,9 +317,10 @@ int tc2_try_prepare(const ConvParams& p, int ksize, int stride, const float* w_o
     plan->tma_epi = tc_epi_with_nbuf(plan->tma_epi, nb) | (tc_epi_want_coalesced(nt) ? kEpiCoalesced : 0);
     epi_bytes = tc_epi_total_bytes(plan->tma_epi, nt);
   } else {
-    plan->tma_epi = 0;                                                  // fp32 tensors: direct epilogue
     if (nt == 64 && bbytes(64) + 4 * stage_bytes > budget) nt = 32;     // fp32 weights are twice the bytes: keep >= 4 stages
     if (bbytes(nt) + 2 * stage_bytes > budget) return 0;
+    // fp32 tensors: TMA epilogue where shared memory allows (tc_epilogue_loop_tma_f32), else the direct epilogue
+    epi_bytes = tc_epi_prepare_f32(p, nt, ptrs_final, budget - bbytes(nt), stage_bytes, plan);
   }
   int stages = std::min(8, (budget - bbytes(nt) - epi_bytes) / stage_bytes);
   plan->kind = 34;

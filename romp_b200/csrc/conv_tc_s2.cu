@@ -61,7 +61,7 @@ conv_tc_s2_kernel(const __grid_constant__ S2Maps maps, const __grid_constant__ T
   uint8_t* sB = smem;
   uint8_t* sA = smem + Cfg::B_BYTES;
   uint8_t* epi_smem = sA + (size_t)stages * Cfg::STAGE_BYTES;       // TMA-epilogue staging tiles, if any
-  uint64_t* full = reinterpret_cast<uint64_t*>(epi_smem + tc_epi_total_bytes(tma_epi, NT));
+  uint64_t* full = reinterpret_cast<uint64_t*>(epi_smem + (EB == 4 ? tc_epi_f32_total_bytes(tma_epi) : tc_epi_total_bytes(tma_epi, NT)));
   uint64_t* empty = full + stages;
   uint64_t* b_full = empty + stages;
   uint64_t* tmem_full = b_full + 1;
@@ -188,6 +188,9 @@ conv_tc_s2_kernel(const __grid_constant__ S2Maps maps, const __grid_constant__ T
       }
       if (nrings == 2) { const int ts = stage; stage = stage_other; stage_other = ts; const uint32_t tp = phase; phase = phase_other; phase_other = tp; }
     }
+  } else if (EB == 4 && tma_epi) {
+    tc_epilogue_loop_tma_f32<NT>(p, epi_maps, tma_epi, epi_smem, res_bar, tmem_base, tmem_full, tmem_empty, s_bias, tiles_x, per_frame,
+                                 num_tiles);
   } else if (EB == 2 && KSPLIT == 1 && NT == 32 && (tma_epi & kEpiCoalesced)) {   // (instantiated for NT = 32 only: register pressure)
     tc_epilogue_loop_coalesced<NT>(p, tma_epi, epi_smem, tmem_base, tmem_full, tmem_empty, s_bias, tiles_x, per_frame, num_tiles);
   } else if (EB == 2 && KSPLIT == 1 && tma_epi) {

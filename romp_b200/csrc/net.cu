@@ -47,6 +47,7 @@ struct Op {
   int coutPad = 0;
   int engine = B200ROMP_ENGINE_SIMT;   // resolved
   TcConvPlan tc;                       // tcgen05 plan (packed weights, tensor maps)
+  int lane = 0;                        // concurrency lane inside the captured CUDA graph (b200romp_net_set_lane)
 };
 
 }  // namespace b200romp
@@ -70,6 +71,13 @@ struct b200romp_net {
   };
   std::map<GraphKey, cudaGraphExec_t> graphs;
   bool use_graph = true;
+  // multi-lane capture: independent ops (the HRNet branches, the three heads) are captured on separate streams so that the
+  // ramp-up / tail of one persistent conv kernel overlaps the body of a kernel of another branch
+  static constexpr int kLanes = 4;
+  cudaStream_t lane_stream[kLanes] = {nullptr, nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> op_done;     // one event per op, recorded on the op's lane during capture
+  cudaEvent_t fork_ev = nullptr;
+  bool use_lanes = false;
 };
 
 static int fill_params(b200romp_net* net, const Op& op, int batch, ConvParams* out) {
@@ -157,6 +165,8 @@ b200romp_net* b200romp_net_create(int device) {
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) net->sm_count = prop.multiProcessorCount;
   const char* ng = getenv("B200ROMP_NO_GRAPH");
   net->use_graph = !(ng && ng[0] == '1');
+  const char* nl = getenv("B200ROMP_LANES");       // multi-lane capture measured 5 % slower than the linear graph: opt-in
+  net->use_lanes = nl && nl[0] == '1';
   return net;
 }
 
@@ -164,6 +174,10 @@ void b200romp_net_destroy(b200romp_net* net) {
   if (!net) return;
   cudaSetDevice(net->device);
   for (auto& kv : net->graphs) cudaGraphExecDestroy(kv.second);
+  for (cudaEvent_t e : net->op_done) cudaEventDestroy(e);
+  if (net->fork_ev) cudaEventDestroy(net->fork_ev);
+  for (int l = 1; l < b200romp_net::kLanes; ++l)
+    if (net->lane_stream[l]) cudaStreamDestroy(net->lane_stream[l]);
   for (void* p : net->device_allocs) cudaFree(p);
   if (net->workspace) cudaFree(net->workspace);
   delete net;
@@ -406,6 +420,72 @@ int b200romp_net_bind(b200romp_net* net, int tensor, void* device_ptr) {
   return B200ROMP_OK;
 }
 
+// Capture-time scheduling: ops are issued in their linear order, each on the stream of its lane.  Cross-lane ordering comes
+// from events on the BUFFERS an op touches (workspace buffers are recycled by the liveness planner, so read-after-write,
+// write-after-read and write-after-write hazards are all tracked at buffer granularity): the op's lane waits for the last
+// writer of everything it reads and for the last writer + all later readers of what it writes.  Inside stream capture the
+// events become graph edges.  An op with a cross-lane wait is launched without the programmatic-dependent-launch attribute.
+static int enqueue_all_lanes(b200romp_net* net, int batch, cudaStream_t stream) {
+  constexpr int L = b200romp_net::kLanes;
+  const size_t n = net->ops.size();
+  if (net->op_done.size() != n) {
+    for (cudaEvent_t e : net->op_done) cudaEventDestroy(e);
+    net->op_done.assign(n, nullptr);
+    for (auto& e : net->op_done) B2R_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  if (!net->fork_ev) B2R_CUDA_OK(cudaEventCreateWithFlags(&net->fork_ev, cudaEventDisableTiming));
+  for (int l = 1; l < L; ++l)
+    if (!net->lane_stream[l]) B2R_CUDA_OK(cudaStreamCreateWithFlags(&net->lane_stream[l], cudaStreamNonBlocking));
+  net->lane_stream[0] = stream;
+  struct Access { int writer = -1; std::vector<int> readers; };
+  std::map<const void*, Access> acc;
+  bool lane_used[L] = {true, false, false, false};
+  B2R_CUDA_OK(cudaEventRecord(net->fork_ev, stream));
+  int rc = B200ROMP_OK;
+  for (size_t i = 0; i < n && rc == B200ROMP_OK; ++i) {
+    Op& op = net->ops[i];
+    const int lane = std::min(std::max(op.lane, 0), L - 1);
+    cudaStream_t st = net->lane_stream[lane];
+    if (!lane_used[lane]) {
+      B2R_CUDA_OK(cudaStreamWaitEvent(st, net->fork_ev, 0));
+      lane_used[lane] = true;
+    }
+    std::vector<const void*> reads;
+    const void* write = net->tensors[op.d.out].ptr;
+    auto add_read = [&](int t) { if (t >= 0 && !net->tensors[t].constant) reads.push_back(net->tensors[t].ptr); };
+    add_read(op.d.in);
+    if (op.kind == 1) for (int k = 0; k < op.sum.n_terms; ++k) add_read(op.sum.term[k]);
+    else add_read(op.d.res);
+    std::vector<int> deps;
+    for (const void* r : reads) { auto it = acc.find(r); if (it != acc.end() && it->second.writer >= 0) deps.push_back(it->second.writer); }
+    { auto it = acc.find(write); if (it != acc.end()) { if (it->second.writer >= 0) deps.push_back(it->second.writer); for (int r : it->second.readers) deps.push_back(r); } }
+    std::sort(deps.begin(), deps.end());
+    deps.erase(std::unique(deps.begin(), deps.end()), deps.end());
+    bool cross = false;
+    for (int d : deps) {
+      const int dl = std::min(std::max(net->ops[d].lane, 0), L - 1);
+      if (dl != lane) { B2R_CUDA_OK(cudaStreamWaitEvent(st, net->op_done[d], 0)); cross = true; }
+    }
+    g_tc_pdl_override = cross ? 0 : -1;
+    rc = enqueue_op(net, op, batch, st);
+    g_tc_pdl_override = -1;
+    if (rc) break;
+    B2R_CUDA_OK(cudaEventRecord(net->op_done[i], st));
+    for (const void* r : reads) acc[r].readers.push_back((int)i);
+    Access& w = acc[write];
+    w.writer = (int)i;
+    w.readers.clear();
+  }
+  // join: the user stream continues after the last op of every lane
+  if (rc == B200ROMP_OK) {
+    int last[L] = {-1, -1, -1, -1};
+    for (size_t i = 0; i < n; ++i) last[std::min(std::max(net->ops[i].lane, 0), L - 1)] = (int)i;
+    for (int l = 1; l < L; ++l)
+      if (last[l] >= 0) B2R_CUDA_OK(cudaStreamWaitEvent(stream, net->op_done[last[l]], 0));
+  }
+  return rc;
+}
+
 static int enqueue_all(b200romp_net* net, int batch, cudaStream_t stream) {
   for (size_t i = 0; i < net->ops.size(); ++i) {
     int rc = enqueue_op(net, net->ops[i], batch, stream);
@@ -432,7 +512,10 @@ int b200romp_net_run(b200romp_net* net, int batch, b200romp_stream stream_) {
       cudaGetLastError();
       return enqueue_all(net, batch, stream);   // stream cannot capture (e.g. legacy default stream)
     }
-    int rc = enqueue_all(net, batch, stream);
+    bool lanes = false;
+    if (net->use_lanes)
+      for (const Op& op : net->ops) lanes = lanes || op.lane != 0;
+    int rc = lanes ? enqueue_all_lanes(net, batch, stream) : enqueue_all(net, batch, stream);
     e = cudaStreamEndCapture(stream, &graph);
     if (rc) {
       if (graph) cudaGraphDestroy(graph);
@@ -521,6 +604,13 @@ int b200romp_net_describe(b200romp_net* net, char* buf, int len) {
   memcpy(buf, s.data(), n);
   buf[n] = 0;
   return n;
+}
+
+int b200romp_net_set_lane(b200romp_net* net, int op, int lane) {
+  B2R_REQUIRE(net && !net->finalized && op >= 0 && op < (int)net->ops.size(), "set_lane: bad op id or net already finalized");
+  B2R_REQUIRE(lane >= 0 && lane < b200romp_net::kLanes, "set_lane: lane must be 0..%d", b200romp_net::kLanes - 1);
+  net->ops[op].lane = lane;
+  return B200ROMP_OK;
 }
 
 int b200romp_net_num_launches(b200romp_net* net) { return net ? (int)net->ops.size() : 0; }

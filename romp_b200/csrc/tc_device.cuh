@@ -561,10 +561,120 @@ __device__ __forceinline__ void tc_epilogue_loop_tma(const ConvParams& p, const 
   __syncwarp();
 }
 
+// ---- TMA epilogue for fp32 tensors (TF32 engine) ---------------------------------------------------------
+// Same idea as tc_epilogue_loop_tma, fp32 elements: the unit of work is one 32-channel CHUNK of one tile (32 pixels x
+// 32 channels x 4 B = 4 KB per epilogue warp, 128 B rows in the SWIZZLE_128B pattern, conflict-free for row-per-thread
+// 16 B accesses).  A warp walks the linear sequence of its chunks (tile-major) through `nbuf` staging buffers:
+//   chunk j: [lane 0] wait until the store that last read buffer (j+1) % nbuf is done, prefetch the residual box of chunk
+//            j+1 into it (TMA load);  wait for the accumulator (first chunk of a tile) and for this chunk's residual;
+//            tcgen05.ld 32 columns -> + bias (+ residual) -> ReLU -> fp32 in place;  fence, one TMA tensor store.
+// Why: the direct fp32 epilogue (thread = pixel, 8 x 16 B stores per 128 B line, 32 lines per warp-wide access) costs
+// ~8x its payload in L1/shared-memory wavefronts, and these kernels are shared-memory-bandwidth bound.
+constexpr int kF32ChunkBytes = 32 * 32 * 4;
+__host__ __device__ constexpr int tc_epi_f32_total_bytes(int tma_epi) { return tma_epi ? kEpiWarps * tc_epi_nbuf(tma_epi) * kF32ChunkBytes : 0; }
+
+template <int NT, bool CTA2 = false>
+__device__ __forceinline__ void tc_epilogue_loop_tma_f32(const ConvParams& p, const TcEpiMaps& maps, int tma_epi, uint8_t* epi_smem,
+                                                         uint64_t* res_bar, uint32_t tmem_base, uint64_t* tmem_full,
+                                                         uint64_t* tmem_empty, const float* s_bias, int tiles_x, int per_frame,
+                                                         int num_tiles) {
+  static_assert(NT % 32 == 0, "chunks of 32 channels");
+  constexpr int NCH = NT / 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ew = warp - kFirstEpiWarp;
+  const int group = ew >> 2;
+  const int q = warp & 3;
+  const int co0 = blockIdx.y * NT;
+  const bool has_res = (tma_epi & kTmaEpiRes) != 0;
+  const int nbuf = tc_epi_nbuf(tma_epi);
+  uint8_t* stg0 = epi_smem + ew * nbuf * kF32ChunkBytes;
+  uint64_t* rbar = &res_bar[ew * 3];
+  constexpr int ACC = AccCfg<1>::ACC;
+  pdl_wait();
+  const uint64_t res_pol = l2_policy_stream(p.debug);
+  const bool relu = p.relu != 0;
+  const uint32_t bias_saddr = smem_u32(s_bias);
+  const int tstep = 2 * (int)gridDim.x;
+  const int first_tile = blockIdx.x + group * gridDim.x;
+  // coordinates of chunk j of this warp: tile = first_tile + (j / NCH) * tstep, channels (j % NCH) * 32
+  auto load_res = [&](int tile, int c, int buf) {   // lane 0 only
+    const int n = tile / per_frame, rem = tile % per_frame;
+    mbar_arrive_expect_tx(&rbar[buf], kF32ChunkBytes);
+    tma_load_4d(stg0 + buf * kF32ChunkBytes, &maps.res, &rbar[buf], p.res_c_off + co0 + c * 32, (rem % tiles_x) * 8,
+                (rem / tiles_x) * 16 + q * 4, n, res_pol);
+  };
+  if (has_res && lane == 0 && first_tile < num_tiles) load_res(first_tile, 0, 0);
+  int it = group, buf = 0;
+  uint32_t rphase = 0;                          // parity of the residual barriers: flips each time the buffer ring wraps
+  for (int tile = first_tile; tile < num_tiles; tile += tstep, it += 2) {
+    const int acc = it & (ACC - 1);
+    const int n = tile / per_frame, rem = tile % per_frame;
+    const int y0 = (rem / tiles_x) * 16 + q * 4, x0 = (rem % tiles_x) * 8;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT);
+#pragma unroll 1
+    for (int c = 0; c < NCH; ++c) {
+      uint8_t* stg = stg0 + buf * kF32ChunkBytes;
+      const int buf_next = buf + 1 == nbuf ? 0 : buf + 1;
+      if (lane == 0) {
+        if (has_res) {
+          if (nbuf == 1) {
+            if (!(tile == first_tile && c == 0)) { bulk_wait_read(0); load_res(tile, c, 0); }
+          } else {
+            bulk_wait_read(nbuf - 2);             // the store that last read buffer buf_next is done
+            const int nt_tile = c + 1 < NCH ? tile : tile + tstep, nc = c + 1 < NCH ? c + 1 : 0;
+            if (nt_tile < num_tiles) load_res(nt_tile, nc, buf_next);
+          }
+        } else {
+          bulk_wait_read(nbuf - 1);               // the store that last read this buffer is done
+        }
+      }
+      __syncwarp();
+      if (c == 0) {
+        mbar_wait(&tmem_full[acc], (it / ACC) & 1);
+        tc_fence_after();
+      }
+      if (has_res) mbar_wait(&rbar[buf], rphase);
+      uint32_t r[32];
+      tmem_ld32(taddr + c * 32, r);
+      tmem_ld_wait();
+      if (c + 1 == NCH) tc_fence_before();        // accumulator fully read (released below)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {               // 8 x 16 B = the 32 channels of this thread's pixel
+        float4 b;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(bias_saddr + (c * 32 + 4 * i) * 4));
+        float4 v = make_float4(__uint_as_float(r[4 * i + 0]) + b.x, __uint_as_float(r[4 * i + 1]) + b.y,
+                               __uint_as_float(r[4 * i + 2]) + b.z, __uint_as_float(r[4 * i + 3]) + b.w);
+        float4* slot = reinterpret_cast<float4*>(stg + lane * 128 + ((i ^ (lane & 7)) * 16));
+        if (has_res) {
+          const float4 t = *slot;
+          v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+        }
+        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        *slot = v;
+      }
+      fence_proxy_async();                        // generic-proxy writes -> visible to the TMA store
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_4d(&maps.out, stg, p.out_c_off + co0 + c * 32, x0, y0, n);
+        bulk_commit_group();
+        if (c + 1 == NCH) {
+          if (CTA2) mbar_arrive_cluster(&tmem_empty[acc], 0);
+          else mbar_arrive(&tmem_empty[acc]);
+        }
+      }
+      if (buf_next == 0) rphase ^= 1;
+      buf = buf_next;
+    }
+  }
+  if (lane == 0) bulk_wait0();                    // all stores performed before the CTA's shared memory goes away
+  __syncwarp();
+}
+
 // launch with the programmatic-stream-serialization attribute (see pdl_trigger / pdl_wait); B200ROMP_NO_PDL=1 disables it
 template <typename... KArgs, typename... Args>
 static inline cudaError_t tc_launch(void (*kern)(KArgs...), dim3 grid, int threads, int smem_bytes, cudaStream_t stream, Args&&... args) {
-  static const bool pdl = [] { const char* e = getenv("B200ROMP_NO_PDL"); return !(e && e[0] == '1'); }();
+  static const bool pdl_default = [] { const char* e = getenv("B200ROMP_NO_PDL"); return !(e && e[0] == '1'); }();
+  const bool pdl = pdl_default && g_tc_pdl_override != 0;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(threads);
@@ -734,6 +844,9 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 PFN_encodeTiled tc_get_encode();
 // decides whether the TMA epilogue applies (sets plan->tma_epi and the out/res tensor maps); 0 = direct epilogue
 int tc_epi_prepare(const ConvParams& p, int nt, bool ptrs_final, TcConvPlan* plan);
+// fp32 variant (TF32 engine): maps with box (32 ch, 8, 4, 1) fp32 SWIZZLE_128B; picks the staging depth for `avail` bytes next to
+// pipeline stages of `stage_bytes`; returns the staging bytes (0 = direct epilogue)
+int tc_epi_prepare_f32(const ConvParams& p, int nt, bool ptrs_final, int avail, int stage_bytes, TcConvPlan* plan);
 // bf16 weight slab in shared-memory-image order [ntile][tap][chunk][NT rows x ROWB] with the TMA/UMMA XOR swizzle
 int tc_pack_weights(const float* w_oihw, int cin, int cout, int taps, int nt, void** d_out, std::vector<void*>* allocs, int rowb, int eb);
 float tc_round_tf32_host(float w);   // fp32 -> TF32, ties away from zero (cvt.rna.tf32.f32)

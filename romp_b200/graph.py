@@ -63,6 +63,23 @@ class NetBuilder:
         self.shape = {}
         self.names = {}
         self.flops_per_frame = 0
+        self.lane = 0
+
+    def on_lane(self, lane):
+        """with nb.on_lane(b): ...  - ops added inside run on concurrency lane b of the captured CUDA graph."""
+        nb = self
+
+        class _Lane:
+            def __enter__(self_):
+                self_.prev, nb.lane = nb.lane, int(lane) % 4
+
+            def __exit__(self_, *exc):
+                nb.lane = self_.prev
+        return _Lane()
+
+    def _added(self, op_id):
+        if self.lane:
+            _lib.check(self.lib.b200romp_net_set_lane(self.net, op_id, self.lane), "set_lane")
 
     def tensor(self, H, W, Cc, dtype=None, nchw=0, external=0, name=None):
         dtype = self.act if dtype is None else dtype
@@ -109,13 +126,13 @@ class NetBuilder:
                           pow_channel, d.engine)
             for dd, ws, bb in ((d0, w[:, :128], bp), (d1, w[:, 128:], None)):
                 ws = np.ascontiguousarray(ws)
-                _lib.check(self.lib.b200romp_net_add_conv(
+                self._added(_lib.check(self.lib.b200romp_net_add_conv(
                     self.net, C.byref(dd), ws.ctypes.data_as(C.POINTER(C.c_float)),
-                    None if bb is None else bb.ctypes.data_as(C.POINTER(C.c_float))), "add_conv")
+                    None if bb is None else bb.ctypes.data_as(C.POINTER(C.c_float))), "add_conv"))
             return out
-        _lib.check(self.lib.b200romp_net_add_conv(
+        self._added(_lib.check(self.lib.b200romp_net_add_conv(
             self.net, C.byref(d), w.ctypes.data_as(C.POINTER(C.c_float)),
-            None if bp is None else bp.ctypes.data_as(C.POINTER(C.c_float))), "add_conv")
+            None if bp is None else bp.ctypes.data_as(C.POINTER(C.c_float))), "add_conv"))
         return out
 
     def sum(self, base, terms, ups, relu=True, out_dtype=None, name=None):
@@ -124,7 +141,7 @@ class NetBuilder:
         out = self.tensor(H, W, Cc, out_dtype, name=name)
         d = SumDesc(out, base, len(terms), (C.c_int * 4)(*(list(terms) + [0] * (4 - len(terms)))),
                     (C.c_int * 4)(*(list(ups) + [1] * (4 - len(ups)))), int(relu))
-        _lib.check(self.lib.b200romp_net_add_sum(self.net, C.byref(d)), "add_sum")
+        self._added(_lib.check(self.lib.b200romp_net_add_sum(self.net, C.byref(d)), "add_sum"))
         return out
 
     def finalize(self, max_batch):
@@ -178,9 +195,16 @@ def build_backbone(nb: NetBuilder, sd, in_dtype):
         of a lower-resolution branch / chain of stride-2 3x3 convs of a higher-resolution one) and ONE sum op per
         output branch adds them in fp32 to the identity term, upsampling on the fly, then ReLU (model.py:243)."""
         xs = list(xs)
+        # The branches are independent (model.py:226-233): branch b is tagged with concurrency lane b.  Lanes are OFF by
+        # default (b200romp_net: B200ROMP_LANES=1 turns them on): measured on B200, capturing the branches on separate
+        # streams LOSES 5 % (6044 vs 6373 frames/s, profiles/r02_bench_b_*lanes.json) - the persistent conv kernels each
+        # fill every SM, so concurrency only interleaves their CTAs, which thrashes L2 (four streamed working sets
+        # instead of one producer->consumer pair) and drops the programmatic-dependent-launch edges at lane crossings.
+        # Ops stay in branch-major order: a conv's output is consumed while still L2-resident.
         for b in range(nbr):
-            for k in range(4):
-                xs[b] = basic_block(xs[b], f"{q}branches.{b}.{k}.")
+            with nb.on_lane(b):
+                for k in range(4):
+                    xs[b] = basic_block(xs[b], f"{q}branches.{b}.{k}.")
         outs = []
         for i in range(nbr if multi else 1):
             terms, ups = [], []
@@ -188,17 +212,19 @@ def build_backbone(nb: NetBuilder, sd, in_dtype):
                 if j == i:
                     continue                  # identity term (model.py:236-239) is the base of the sum
                 r = f"{q}fuse_layers.{i}.{j}."
-                if j > i:                     # 1x1 conv + BN, nearest upsample folded into the sum (model.py:188-197)
-                    terms.append(cb(xs[j], r + "0", r + "1"))
-                    ups.append(2 ** (j - i))
-                else:                         # chain of stride-2 3x3 convs (model.py:200-218)
-                    t = xs[j]
-                    for k in range(i - j - 1):
-                        t = cb(t, f"{r}{k}.0", f"{r}{k}.1", stride=2, relu=True)
-                    k = i - j - 1
-                    terms.append(cb(t, f"{r}{k}.0", f"{r}{k}.1", stride=2))
-                    ups.append(1)
-            acc = nb.sum(xs[i], terms, ups, relu=True)
+                with nb.on_lane(j):           # a fuse term is computed from branch j alone
+                    if j > i:                 # 1x1 conv + BN, nearest upsample folded into the sum (model.py:188-197)
+                        terms.append(cb(xs[j], r + "0", r + "1"))
+                        ups.append(2 ** (j - i))
+                    else:                     # chain of stride-2 3x3 convs (model.py:200-218)
+                        t = xs[j]
+                        for k in range(i - j - 1):
+                            t = cb(t, f"{r}{k}.0", f"{r}{k}.1", stride=2, relu=True)
+                        k = i - j - 1
+                        terms.append(cb(t, f"{r}{k}.0", f"{r}{k}.1", stride=2))
+                        ups.append(1)
+            with nb.on_lane(i):
+                acc = nb.sum(xs[i], terms, ups, relu=True)
             outs.append(acc)
         return outs
 
@@ -245,17 +271,18 @@ def build_romp(sd, device=0, precision="bf16", in_dtype=U8, max_batch=64, engine
                   name="head_in")
     center_maps = nb.tensor(64, 64, 1, F32, nchw=1, external=1, name="center_maps")
     params_maps = nb.tensor(64, 64, 145, F32, nchw=1, external=1, name="params_maps")
-    for s, h in enumerate(order):
+    for s, h in enumerate(order):                          # the three heads are independent: one (optional) lane each
         q = f"final_layers.{h}."
-        y = basic_block(hin, q + "1.0.0.", in_c_off=64 * s, res_c_off=64 * s)
-        y = basic_block(y, q + "1.1.0.")
-        w, b = fold_bn(sd, q + "2", None)
-        if h == 3:      # cam maps -> params_maps[:, 0:3], cam scale 1.1**x (model.py:480, main.py:113)
-            nb.conv(y, w, b, out=params_maps, out_c_off=0, pow_channel=0)
-        elif h == 1:    # params maps -> params_maps[:, 3:145]
-            nb.conv(y, w, b, out=params_maps, out_c_off=3)
-        else:
-            nb.conv(y, w, b, out=center_maps)
+        with nb.on_lane(s):
+            y = basic_block(hin, q + "1.0.0.", in_c_off=64 * s, res_c_off=64 * s)
+            y = basic_block(y, q + "1.1.0.")
+            w, b = fold_bn(sd, q + "2", None)
+            if h == 3:      # cam maps -> params_maps[:, 0:3], cam scale 1.1**x (model.py:480, main.py:113)
+                nb.conv(y, w, b, out=params_maps, out_c_off=0, pow_channel=0)
+            elif h == 1:    # params maps -> params_maps[:, 3:145]
+                nb.conv(y, w, b, out=params_maps, out_c_off=3)
+            else:
+                nb.conv(y, w, b, out=center_maps)
     nb.finalize(max_batch)
     return nb, dict(frames=frames, center_maps=center_maps, params_maps=params_maps)
 

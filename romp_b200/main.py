@@ -197,9 +197,14 @@ class ROMP(torch.nn.Module):
         self.settings = s = romp_settings
         if not torch.cuda.is_available() or s.GPU < 0:
             raise RuntimeError("romp_b200.ROMP needs a CUDA device (B200, sm_100a); there is no CPU fallback")
-        for flag in ("onnx", "temporal_optimize", "render_mesh", "show", "show_largest"):
+        for flag in ("render_mesh", "show"):
             if getattr(s, flag, False):
                 raise NotImplementedError(f"--{flag} is outside the B200 hot path (SURVEY.md section 2: out of scope)")
+        if getattr(s, "onnx", False):
+            raise NotImplementedError("--onnx: onnxruntime is not available offline; seam S1 is ROMP.model (MapsModule), the same "
+                                      "seam the reference swaps for its ONNX session (main.py:78-91,108-110)")
+        if getattr(s, "show_largest", False) and not getattr(s, "temporal_optimize", False):
+            raise NotImplementedError("--show_largest only selects the smoothed person of --temporal_optimize (main.py:128-134)")
         self.lib = _lib.load()
         self.device_index = int(s.GPU)
         self.tdevice = torch.device("cuda", self.device_index)
@@ -218,6 +223,15 @@ class ROMP(torch.nn.Module):
             self.smpl = SMPLParser(smpl_pack, self.device_index)
         self._alloc(self.max_batch)
         self.model = MapsModule(self)
+        self.temporal = None
+        if getattr(s, "temporal_optimize", False):                                 # main.py:117-125
+            from .temporal import TemporalState
+            self.temporal = TemporalState(bool(getattr(s, "show_largest", False)))
+            self._tracks = self.lib.b200romp_tracks_create(self.device_index, self.temporal.n_slots)
+            if not self._tracks:
+                raise RuntimeError("b200romp_tracks_create: " + self.lib.b200romp_last_error().decode())
+            self._slot_host = torch.zeros(self.cap, dtype=torch.int32).pin_memory()
+            self._slot_dev = torch.zeros(self.cap, dtype=torch.int32, device=self.tdevice)
 
     # ------------------------------------------------------------------------------------------
     def _net(self, in_dtype):
@@ -281,8 +295,8 @@ class ROMP(torch.nn.Module):
         return self.shared["center_maps"][:B], self.shared["params_maps"][:B]
 
     @torch.no_grad()
-    def run_post(self, B, offsets, center_override=None, slot=None):
-        """Seams S2-S4 on the maps currently in the buffers; everything enqueued on self.stream, no host sync."""
+    def run_parse(self, B, center_override=None, slot=None):
+        """Seam S2 on the maps currently in the buffers (enqueued on self.stream, no host sync)."""
         sh, lib, sp = self.shared, self.lib, C.c_void_p(self.stream.cuda_stream)
         b = (self.slots[self._slot] if slot is None else slot)["dev"]
         center = sh["center_maps"] if center_override is None else center_override
@@ -290,16 +304,29 @@ class ROMP(torch.nn.Module):
                                       self.cap, _ptr(b["count"]), _ptr(b["batch_ids"]), _ptr(sh["flat_inds"]),
                                       _ptr(b["center_confs"]), _ptr(sh["params_pred"]), _ptr(b["cam"]), _ptr(b["thetas"]),
                                       _ptr(b["betas"]), _ptr(b["center_preds"]), _ptr(sh["parse_ws"]), sp), "parse")
-        cap = B * MAX_PERSON
+
+    @torch.no_grad()
+    def run_smpl_project(self, cap, offsets, slot=None, count_on_device=True):
+        """Seams S3-S4 for up to ``cap`` persons (the device-side count limits it further unless count_on_device=False)."""
+        sh, lib, sp = self.shared, self.lib, C.c_void_p(self.stream.cuda_stream)
+        b = (self.slots[self._slot] if slot is None else slot)["dev"]
+        cnt = b["count"] if count_on_device else None
+        cp = None if cnt is None else _ptr(cnt)
         off = (C.c_float * 6)(*[float(v) for v in offsets])
         if self.calc_smpl:
-            self.smpl.forward(b["betas"], b["thetas"], cap, b["count"], self.settings.root_align, sh["smpl_ws"],
+            self.smpl.forward(b["betas"], b["thetas"], cap, cnt, self.settings.root_align, sh["smpl_ws"],
                               b["verts"], b["joints"], self.stream.cuda_stream)
-            _lib.check(lib.b200romp_project(_ptr(b["joints"]), None, _ptr(b["cam"]), cap, _ptr(b["count"]), off,
+            _lib.check(lib.b200romp_project(_ptr(b["joints"]), None, _ptr(b["cam"]), cap, cp, off,
                                             _ptr(b["pj2d_org"]), None, None, _ptr(b["cam_trans"]), sp), "project")
         else:   # without SMPL the reference keeps the weak-perspective translation of main.py:166
-            _lib.check(lib.b200romp_project(_ptr(b["cam"]), None, _ptr(b["cam"]), cap, _ptr(b["count"]), off, None, None,
+            _lib.check(lib.b200romp_project(_ptr(b["cam"]), None, _ptr(b["cam"]), cap, cp, off, None, None,
                                             _ptr(b["cam_trans"]), None, sp), "project")
+
+    @torch.no_grad()
+    def run_post(self, B, offsets, center_override=None, slot=None):
+        """Seams S2-S4 on the maps currently in the buffers; everything enqueued on self.stream, no host sync."""
+        self.run_parse(B, center_override, slot)
+        self.run_smpl_project(B * MAX_PERSON, offsets, slot)
 
     def _views(self, src, n):
         out = {"cam": src["cam"][:n], "global_orient": src["thetas"][:n, :3], "body_pose": src["thetas"][:n, 3:],
@@ -481,6 +508,8 @@ class ROMP(torch.nn.Module):
         slot = self.slots[self._slot]
         fd = self._staging(slot, torch.uint8, 1)
         _, pad_info = self.preprocess(image, out=fd[0])
+        if self.temporal is not None:
+            return self._forward_temporal(fd, pad_info, slot, signal_ID)
         with torch.cuda.stream(self.stream):
             self.run_maps(fd)
             self.run_post(1, pad_info)
@@ -494,6 +523,64 @@ class ROMP(torch.nn.Module):
         if getattr(self.settings, "cam_trans", "lsq") == "pnp" and self.calc_smpl:
             out["cam_trans"] = estimate_translation_pnp(out["joints"], out["cam"])
         return out
+
+
+    @torch.no_grad()
+    def _forward_temporal(self, fd, pad_info, slot, signal_ID):
+        """forward() with --temporal_optimize (main.py:164-165 -> temporal_optimization :127-157): parse, associate the
+        detections with tracks on the host (needs the cams: one small D2H, like the reference), One-Euro smoothing of
+        thetas / betas / cam on the device, then SMPL + projection on the smoothed parameters."""
+        b, lib, sp = slot["dev"], self.lib, C.c_void_p(self.stream.cuda_stream)
+        with torch.cuda.stream(self.stream):
+            self.run_maps(fd)
+            self.run_parse(1, None, slot)
+            slot["count_host"].copy_(b["count"], non_blocking=True)
+        self.stream.synchronize()
+        n = int(slot["count_host"].item())
+        if n == 0:
+            print("None person detected")
+            return None
+        with torch.cuda.stream(self.stream):
+            cams = b["cam"][:n].cpu().numpy()
+            raw_thetas = b["thetas"][:n].clone()          # global_orient / body_pose keep the UNsmoothed values (main.py:148-153)
+        slots, track_ids, reset = self.temporal.assign(cams, signal_ID)
+        for sl in reset:
+            _lib.check(lib.b200romp_tracks_reset(self._tracks, int(sl), sp), "tracks_reset")
+        self._slot_host[:n].copy_(torch.from_numpy(slots))
+        n_smpl = n
+        with torch.cuda.stream(self.stream):
+            self._slot_dev[:n].copy_(self._slot_host[:n], non_blocking=True)
+            _lib.check(lib.b200romp_one_euro_smooth(self._tracks, _ptr(self._slot_dev), n, None, _ptr(b["thetas"]), _ptr(b["betas"]),
+                                                    10, 10, _ptr(b["cam"]), float(self.settings.smooth_coeff), 30.0, sp), "one_euro")
+            if self.temporal.show_largest:                 # only the largest person goes on (main.py:129-134)
+                k = int(np.argmax(cams[:, 0]))
+                for key in ("thetas", "betas", "cam"):
+                    b[key][0].copy_(b[key][k].clone())
+                n_smpl = 1
+            self.run_smpl_project(n_smpl, pad_info, slot, count_on_device=False)
+            slot["done"].record(self.stream)
+            host = self._host(slot)
+            for key, v in b.items():
+                if key != "count":
+                    host[key][:n].copy_(v[:n], non_blocking=True)
+            raw_host = raw_thetas.cpu()
+        self.stream.synchronize()
+        v = {k: np.array(t.numpy()) for k, t in self._views(host, n).items()}
+        v.pop("pred_batch_ids")
+        v["global_orient"], v["body_pose"] = raw_host.numpy()[:, :3].copy(), raw_host.numpy()[:, 3:].copy()
+        for key in ("smpl_thetas", "smpl_betas", "cam", "cam_trans", "verts", "joints", "pj2d_org"):
+            if key in v:
+                v[key] = v[key][:n_smpl]
+        if track_ids is not None:
+            v["track_ids"] = track_ids                      # main.py:156
+        return v
+
+    def __del__(self):
+        try:
+            if getattr(self, "_tracks", None):
+                self.lib.b200romp_tracks_destroy(self._tracks)
+        except Exception:
+            pass
 
 
 default_settings = None   # the reference evaluates romp_settings([]) at import (main.py:62); we do not

@@ -123,3 +123,17 @@ def test_cfg1_resnet50_plumbing(golden_dir):
     assert len(out["cam"]) == 1 and out["center_preds"].tolist() == [[160, 240]]
     v, j = O.smpl_forward(synth.smpl_pack(0), out["smpl_betas"], out["smpl_thetas"])
     assert v.shape == (1, 6890, 3) and j.shape == (1, 71, 3) and torch.isfinite(v).all()
+
+
+def test_one_euro(golden_dir):
+    """Row f4: oracle/temporal_oracle.py against the reference's smooth_results / OneEuroFilter outputs (one_euro.npz)."""
+    from oracle import temporal_oracle as T
+    z = g(golden_dir, "one_euro.npz")
+    Tn, P = z["thetas"].shape[:2]
+    filters = [T.make_filters(3.0) for _ in range(P)]
+    err = 0.0
+    for t in range(Tn):
+        for p in range(P):
+            a, b, c = T.smooth(filters[p], z["thetas"][t, p], z["betas"][t, p], z["cam"][t, p])
+            err = max(err, np.abs(a - z["out_thetas"][t, p]).max(), np.abs(b - z["out_betas"][t, p]).max(), np.abs(c - z["out_cam"][t, p]).max())
+    assert err < 2e-5, err
