@@ -59,7 +59,8 @@ typedef struct b200romp_conv_desc {
   int res, res_c_off;      /* residual tensor id or -1, first residual channel                          */
   int res_broadcast;       /* 1 = residual has no batch dimension (per-pixel bias map)                  */
   int cin, cout;           /* channels consumed / produced                                              */
-  int ksize, stride;       /* 1|3, 1|2 (padding = ksize/2)                                              */
+  int ksize, stride;       /* 1|3|7 (padding = ksize/2), stride 1|2; 13 = Conv1d 1x3 along W (BEV); 42 = ConvTranspose2d(4, stride 2,
+                              padding 1) with weight [cin][cout][4][4] (ResNet-50 deconv layers, resnet_50.py:93-120)     */
   int relu;                /* 1 = ReLU after the residual add                                           */
   int upsample;            /* 1, 2, 4, 8: nearest-neighbour replication of each conv output             */
   int input_norm;          /* 1 = input tensor holds raw 0..255 frames: x/255*2-1 on load (model.py:384) */
@@ -91,6 +92,8 @@ typedef struct b200romp_sum_desc {
 } b200romp_sum_desc;
 /* Returns op id (ops run in the order they were added, convs and sums alike). */
 int b200romp_net_add_sum(b200romp_net* net, const b200romp_sum_desc* desc);
+/* MaxPool2d(kernel 3, stride 2, padding 1) of the ResNet-50 stem (romp/lib/models/resnet_50.py:42): out [ceil(H/2), ceil(W/2), C]. */
+int b200romp_net_add_maxpool(b200romp_net* net, int in, int out);
 /* Concurrency lane (0..3) of an op inside the captured CUDA graph: ops of different lanes that do not depend on each other
  * through a tensor (or a recycled workspace buffer) may overlap - the parallel branches of a HighResolutionModule
  * (model.py:226-233) and the three ROMP heads (model.py:475-478).  Default lane 0.  Call before finalize. */
@@ -189,8 +192,9 @@ typedef struct b200romp_bev_weights {   /* host fp32 arrays */
 b200romp_bev* b200romp_bev_create(int device, const b200romp_bev_weights* w);
 void b200romp_bev_destroy(b200romp_bev* bev);
 /* summon_feats = cat([center_fv, cam_offset, img_feats],1).view(B,2560,128) (bev/model.py:190), stored as the NHWC
- * "image" [B,1,128(w),2560] consumed by the Conv1d graph.  maps_fv [B,4,128,128] fp32 NCHW, img_feats [B,128,128,16]. */
-int b200romp_bev_bv_input(const float* maps_fv, const void* img_feats, int feats_dtype, int batch, void* out, int out_dtype,
+ * "image" [B,1,128(w),2560] consumed by the Conv1d graph.  maps_fv [B,4,128,128] fp32 NCHW, img_feats [B,128,128,feats_C]
+ * whose first 16 channels are bv_pre_layers' output (feats_C = 32 when that stack runs zero-padded on the tcgen05 engine). */
+int b200romp_bev_bv_input(const float* maps_fv, const void* img_feats, int feats_dtype, int feats_C, int batch, void* out, int out_dtype,
                           b200romp_stream stream);
 /* center_maps_3d [B,64,128,128] = refiner(center_fv (x) center_bv) (bev/model.py:195-196,206); bv_out = output of
  * bv_out_layers as NHWC [B,1,128(w),128(ch)] (ch < 64: center_maps_bv, >= 64: cam_maps_offset_bv); tmp: same size scratch. */

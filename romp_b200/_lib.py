@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "lib", "libb200romp.so")
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["net.cu", "conv_simt.cu", "conv_tc.cu", "conv_tc_s2.cu", "conv_stem_tc.cu", "conv_tc_2cta.cu", "parse.cu", "smpl.cu", "project.cu", "bev.cu", "pack.cu", "preproc.cu", "temporal.cu"]
+SOURCES = ["net.cu", "conv_simt.cu", "conv_tc.cu", "conv_tc_s2.cu", "conv_stem_tc.cu", "conv_tc_2cta.cu", "conv1d_tc.cu", "parse.cu", "smpl.cu", "project.cu", "bev.cu", "pack.cu", "preproc.cu", "temporal.cu", "resnet_ops.cu"]
 
 F32, BF16, U8 = 0, 1, 2
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, ENGINE_TF32 = 0, 1, 2, 3
@@ -127,6 +127,7 @@ def load():
     _sig(lib.b200romp_net_add_conv, i32, vp, C.POINTER(ConvDesc), fp, fp)
     _sig(lib.b200romp_net_add_sum, i32, vp, C.POINTER(SumDesc))
     _sig(lib.b200romp_net_set_lane, i32, vp, i32, i32)
+    _sig(lib.b200romp_net_add_maxpool, i32, vp, i32, i32)
     _sig(lib.b200romp_net_finalize, i32, vp, i32)
     _sig(lib.b200romp_net_bind, i32, vp, i32, vp)
     _sig(lib.b200romp_net_run, i32, vp, i32, vp)
@@ -145,7 +146,7 @@ def load():
     _sig(lib.b200romp_project, i32, vp, vp, vp, i32, vp, fp, vp, vp, vp, vp, vp)
     _sig(lib.b200romp_bev_create, vp, i32, C.POINTER(BevWeights))
     _sig(lib.b200romp_bev_destroy, None, vp)
-    _sig(lib.b200romp_bev_bv_input, i32, vp, vp, i32, i32, vp, i32, vp)
+    _sig(lib.b200romp_bev_bv_input, i32, vp, vp, i32, i32, i32, vp, i32, vp)
     _sig(lib.b200romp_bev_center3d, i32, vp, vp, vp, i32, i32, vp, vp, vp)
     _sig(lib.b200romp_bev_parse_workspace_bytes, i64, i32)
     _sig(lib.b200romp_bev_parse3d, i32, vp, i32, f32, i32, vp, vp, vp, vp, vp, vp)
@@ -174,7 +175,7 @@ def check(rc, what=""):
 EXPORTS = [
     "b200romp_version", "b200romp_last_error", "b200romp_device_info", "b200romp_net_create",
     "b200romp_net_destroy", "b200romp_net_add_tensor", "b200romp_net_add_const_tensor", "b200romp_net_add_conv",
-    "b200romp_net_add_sum", "b200romp_net_set_lane",
+    "b200romp_net_add_sum", "b200romp_net_set_lane", "b200romp_net_add_maxpool",
     "b200romp_net_finalize", "b200romp_net_bind", "b200romp_net_run", "b200romp_net_read_tensor",
     "b200romp_net_describe", "b200romp_net_num_launches", "b200romp_net_workspace_bytes", "b200romp_net_profile",
     "b200romp_conv2d",

@@ -39,14 +39,14 @@ struct BevDev {
 
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bev_bv_input_kernel(const float* __restrict__ maps_fv, const void* __restrict__ feats,
-                                                           int feats_dtype, int B, void* __restrict__ out, int out_dtype) {
+                                                           int feats_dtype, int feats_C, int B, void* __restrict__ out, int out_dtype) {
   const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x;
   if (idx >= (size_t)B * kS * 2560) return;
   const int ch = idx % 2560, w = (idx / 2560) % kS, b = idx / ((size_t)2560 * kS);
   const int c = ch / kS, h = ch % kS;
   float v;
   if (c < 4) v = maps_fv[(((size_t)b * 4 + c) * kS + h) * kS + w];
-  else v = load_as_float(feats, (((size_t)b * kS + h) * kS + w) * 16 + (c - 4), feats_dtype);
+  else v = load_as_float(feats, (((size_t)b * kS + h) * kS + w) * feats_C + (c - 4), feats_dtype);
   store_from_float(out, idx, out_dtype, v);
 }
 
@@ -76,6 +76,88 @@ __global__ void __launch_bounds__(256) bev_center3d_kernel(const float* __restri
         acc = fmaf(wgt[(dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)], x, acc);
       }
   out[idx] = stage == 1 ? fmaxf(acc, 0.f) : acc + cm_at(maps_fv, bv, bv_dtype, b, d, h, w);
+}
+
+// Fused version of the two stages above (round 2): one kernel, the intermediate t1 never leaves shared memory, and stage 1
+// uses the rank-1 structure of its input: cm[d,h,w] = fv[h,w] * bv[w,d], so
+//     conv1(cm)[d,h,w] = sum_{a,c} bv[w+c, d+a] * G[a,c][h, w+c],   G[a,c][h,x] = sum_b k1[a,b,c] * fv[h+b, x]
+// (9 FMA per voxel instead of 27; G is 9 planes of the block's 10 x 36 footprint).  Stage 2 is the full 27-tap stencil on the
+// shared-memory t1 tile with a sliding window along d.  Block = 8 (d) x 8 (h) x 32 (w) outputs, 256 threads.
+// FLOPs per output: 9 * (10*10*34)/(8*8*32) + 27 = 42 (was 54), global traffic: one fp32 store per voxel (was 3 accesses).
+constexpr int kTD = 8, kTH = 8, kTW = 32;
+__global__ void __launch_bounds__(256) bev_center3d_fused_kernel(const float* __restrict__ maps_fv, const void* __restrict__ bv,
+                                                                 int bv_dtype, BevDev m, float* __restrict__ out) {
+  __shared__ float s_fv[kTH + 4][kTW + 4];            // fv rows h0-2 .. h0+9, cols w0-2 .. w0+33 (zero outside the map)
+  __shared__ float s_bv[kTW + 4][kTD + 4];            // bv[w][d] cols w0-2.., depth d0-2 .. d0+9 (zero outside)
+  __shared__ float s_G[9][kTH + 2][kTW + 4];          // G[a*3+c][h0-1 .. h0+8][w0-2 .. w0+33]
+  __shared__ float s_t1[kTD + 2][kTH + 2][kTW + 2];   // relu(conv1 + b1) on the halo tile, zero outside the volume
+  const int b = blockIdx.z;
+  const int w0 = (blockIdx.x % (kS / kTW)) * kTW, h0 = (blockIdx.x / (kS / kTW)) * kTH, d0 = blockIdx.y * kTD;
+  const int tid = threadIdx.x;
+  const float* cfv = maps_fv + (size_t)b * 4 * kS * kS;            // channel 0 = center_maps_fv
+  for (int i = tid; i < (kTH + 4) * (kTW + 4); i += 256) {
+    const int r = i / (kTW + 4), c = i % (kTW + 4), h = h0 - 2 + r, w = w0 - 2 + c;
+    s_fv[r][c] = (h >= 0 && h < kS && w >= 0 && w < kS) ? cfv[(size_t)h * kS + w] : 0.f;
+  }
+  for (int i = tid; i < (kTW + 4) * (kTD + 4); i += 256) {
+    const int c = i / (kTD + 4), r = i % (kTD + 4), w = w0 - 2 + c, d = d0 - 2 + r;
+    s_bv[c][r] = (w >= 0 && w < kS && d >= 0 && d < kD) ? load_as_float(bv, ((size_t)b * kS + w) * kS + d, bv_dtype) : 0.f;
+  }
+  __syncthreads();
+  const float* k1 = m.center_ref;                       // [27] then b1
+  for (int i = tid; i < 9 * (kTH + 2) * (kTW + 4); i += 256) {
+    const int x = i % (kTW + 4), r = (i / (kTW + 4)) % (kTH + 2), ac = i / ((kTW + 4) * (kTH + 2));
+    const int a = ac / 3, c = ac % 3;
+    // G[a,c][h0-1+r][w0-2+x] = sum_b k1[a][b][c] * fv[h0-1+r + (b-1)][.]  (s_fv row index = r + b)
+    s_G[ac][r][x] = k1[a * 9 + 0 * 3 + c] * s_fv[r + 0][x] + k1[a * 9 + 1 * 3 + c] * s_fv[r + 1][x] + k1[a * 9 + 2 * 3 + c] * s_fv[r + 2][x];
+  }
+  __syncthreads();
+  const float b1 = k1[27];
+  for (int i = tid; i < (kTH + 2) * (kTW + 2); i += 256) {      // one (h, w) column of the t1 halo tile per iteration
+    const int wl = i % (kTW + 2), hl = i / (kTW + 2);            // t1 position (h0-1+hl, w0-1+wl); s_G / s_bv column index = wl + 1 + (c-1)
+    const int h = h0 - 1 + hl, w = w0 - 1 + wl;
+    const bool inside_hw = h >= 0 && h < kS && w >= 0 && w < kS;
+    float g[9];
+#pragma unroll
+    for (int ac = 0; ac < 9; ++ac) g[ac] = s_G[ac][hl][wl + (ac % 3)];
+#pragma unroll
+    for (int dl = 0; dl < kTD + 2; ++dl) {                       // t1 depth d0-1+dl; s_bv depth index = dl + 1 + (a-1)
+      float acc = b1;
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc = fmaf(s_bv[wl + c][dl + a], g[a * 3 + c], acc);
+      const int d = d0 - 1 + dl;
+      s_t1[dl][hl][wl] = (inside_hw && d >= 0 && d < kD) ? fmaxf(acc, 0.f) : 0.f;
+    }
+  }
+  __syncthreads();
+  const float* k2 = m.center_ref + 28;                  // [27] then b2
+  float wk[27];
+#pragma unroll
+  for (int i = 0; i < 27; ++i) wk[i] = k2[i];
+  const float b2 = k2[27];
+  const int wl = tid % kTW, hl = tid / kTW;             // output (h0+hl, w0+wl), all kTD depths
+  float p0[9], p1[9], p2[9];                            // t1 planes d-1, d, d+1 (3x3 in h, w)
+#pragma unroll
+  for (int j = 0; j < 9; ++j) { p0[j] = s_t1[0][hl + j / 3][wl + j % 3]; p1[j] = s_t1[1][hl + j / 3][wl + j % 3]; }
+  const float fvv = s_fv[hl + 2][wl + 2];
+#pragma unroll
+  for (int dl = 0; dl < kTD; ++dl) {
+#pragma unroll
+    for (int j = 0; j < 9; ++j) p2[j] = s_t1[dl + 2][hl + j / 3][wl + j % 3];
+    float acc = b2;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) acc = fmaf(wk[j], p0[j], acc);
+#pragma unroll
+    for (int j = 0; j < 9; ++j) acc = fmaf(wk[9 + j], p1[j], acc);
+#pragma unroll
+    for (int j = 0; j < 9; ++j) acc = fmaf(wk[18 + j], p2[j], acc);
+    const float cm = fvv * s_bv[wl + 2][dl + 2];
+    out[(((size_t)b * kD + d0 + dl) * kS + h0 + hl) * kS + w0 + wl] = acc + cm;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) { p0[j] = p1[j]; p1[j] = p2[j]; }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -458,11 +540,11 @@ void b200romp_bev_destroy(b200romp_bev* h) {
   delete h;
 }
 
-int b200romp_bev_bv_input(const float* maps_fv, const void* img_feats, int feats_dtype, int batch, void* out, int out_dtype,
+int b200romp_bev_bv_input(const float* maps_fv, const void* img_feats, int feats_dtype, int feats_C, int batch, void* out, int out_dtype,
                           b200romp_stream stream) {
-  B2R_REQUIRE(maps_fv && img_feats && out && batch > 0, "bev_bv_input: bad arguments");
+  B2R_REQUIRE(maps_fv && img_feats && out && batch > 0 && feats_C >= 16, "bev_bv_input: bad arguments");
   const size_t n = (size_t)batch * kS * 2560;
-  bev_bv_input_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(maps_fv, img_feats, feats_dtype, batch, out, out_dtype);
+  bev_bv_input_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(maps_fv, img_feats, feats_dtype, feats_C, batch, out, out_dtype);
   B2R_CUDA_OK(cudaGetLastError());
   return B200ROMP_OK;
 }
@@ -470,10 +552,16 @@ int b200romp_bev_bv_input(const float* maps_fv, const void* img_feats, int feats
 int b200romp_bev_center3d(b200romp_bev* h, const float* maps_fv, const void* bv_out, int bv_dtype, int batch, float* tmp,
                           float* center3d, b200romp_stream stream) {
   B2R_REQUIRE(h && maps_fv && bv_out && tmp && center3d && batch > 0, "bev_center3d: bad arguments");
-  const size_t n = (size_t)batch * kVol;
-  const unsigned g = (unsigned)((n + 255) / 256);
-  bev_center3d_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(maps_fv, bv_out, bv_dtype, h->dev, batch, nullptr, tmp, 1);
-  bev_center3d_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(maps_fv, bv_out, bv_dtype, h->dev, batch, tmp, center3d, 2);
+  static const bool two_pass = [] { const char* e = getenv("B200ROMP_BEV_CENTER3D_2PASS"); return e && e[0] == '1'; }();
+  if (two_pass) {                      // round-1 formulation (one thread per voxel, intermediate in `tmp`): kept for A/B checks
+    const size_t n = (size_t)batch * kVol;
+    const unsigned g = (unsigned)((n + 255) / 256);
+    bev_center3d_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(maps_fv, bv_out, bv_dtype, h->dev, batch, nullptr, tmp, 1);
+    bev_center3d_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(maps_fv, bv_out, bv_dtype, h->dev, batch, tmp, center3d, 2);
+  } else {
+    dim3 grid((kS / kTW) * (kS / kTH), kD / kTD, batch);
+    bev_center3d_fused_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(maps_fv, bv_out, bv_dtype, h->dev, center3d);
+  }
   B2R_CUDA_OK(cudaGetLastError());
   return B200ROMP_OK;
 }

@@ -141,5 +141,17 @@ int launch_fuse_sum(const SumParams& p, cudaStream_t stream);
 
 // engines implemented in other translation units
 int launch_conv_simt(const ConvParams& p, int ksize, int stride, cudaStream_t stream);
+// ResNet-50 variant only (resnet_ops.cu): generic k x k conv (7x7 stem), ConvTranspose2d(4,2,1), MaxPool2d(3,2,1)
+int launch_conv_generic(const ConvParams& p, int ksize, int stride, cudaStream_t stream);
+int launch_deconv4x4s2(const ConvParams& p, cudaStream_t stream);
+int launch_maxpool3x3s2(const void* in, void* out, int dtype, int B, int Hin, int Win, int C, cudaStream_t stream);
+// conv-output geometry for a ksize code: 1 / 3 / 7 = square kernels (pad k/2), 13 = Conv1d 1x3, 42 = ConvTranspose2d(4,2,1)
+static inline void conv_out_hw(int ksize, int stride, int H, int W, int* Ho, int* Wo) {
+  if (ksize == 42) { *Ho = 2 * H; *Wo = 2 * W; return; }
+  const int kh = ksize == 13 ? 1 : ksize, kw = ksize == 13 ? 3 : ksize;
+  *Ho = (H + 2 * (kh / 2) - kh) / stride + 1;
+  *Wo = (W + 2 * (kw / 2) - kw) / stride + 1;
+}
+static inline int conv_taps(int ksize) { return ksize == 13 ? 3 : (ksize == 42 ? 16 : ksize * ksize); }
 
 }  // namespace b200romp

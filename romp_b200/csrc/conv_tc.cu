@@ -400,10 +400,11 @@ int tc_epi_prepare_f32(const ConvParams& p, int nt, bool ptrs_final, int avail, 
   }
   const int flags = kTmaEpiOut | (res_tma ? kTmaEpiRes : 0);
   // staging depth: 3 buffers with a residual (compute / prefetch / store in flight), 2 without, while >= 4 pipeline stages
-  // remain, else 2 buffers; a plan that cannot keep 4 stages next to two buffers per warp uses the direct epilogue (measured:
-  // 256->256 @16x16 with one buffer and 3 stages 118 us against 88 us for the direct epilogue with 6 stages)
+  // remain, then while >= 3 remain; never a single buffer: a plan that cannot keep 3 stages next to two buffers per warp uses
+  // the direct epilogue (measured: 256->256 @16x16 with one buffer and 3 stages 118 us against 88 us direct with 6 stages;
+  // 64->64 @64x64 with two buffers and 3 stages 43-50 us against 68 us direct)
   const int want = res_tma ? 3 : 2;
-  for (int min_stages = 4; min_stages >= 4; --min_stages)
+  for (int min_stages = 4; min_stages >= 3; --min_stages)
     for (int nb = want; nb >= 2; --nb) {
       const int bytes = kEpiWarps * nb * kF32ChunkBytes;
       if ((avail - bytes) / stage_bytes >= min_stages) {

@@ -19,6 +19,8 @@ struct TcConvPlan {
   alignas(64) unsigned char tmap_s2[4][128];  // stride-2: one map per input parity (ph,pw)
   alignas(64) unsigned char tmap_epi[2][128]; // TMA epilogue: output / residual tensor (box NT x 8 x 4 x 1)
   int tma_epi = 0;              // bit 0: output through a TMA store, bit 1: residual through a TMA load
+  const void* encoded_in = nullptr;   // conv1d engine: input pointer / batch the tensor map was encoded for (external inputs)
+  int encoded_batch = 0;
   std::string describe() const;
 };
 
@@ -33,6 +35,10 @@ int tc_conv_launch(const TcConvPlan& plan, const ConvParams& p, cudaStream_t str
 int tc2_try_prepare(const ConvParams& p, int ksize, int stride, const float* w_oihw, int sm_count, bool ptrs_final, TcConvPlan* plan,
                     std::vector<void*>* allocs);
 int tc2_launch(const TcConvPlan& plan, const ConvParams& p, cudaStream_t stream);
+// Conv1d (ksize code 13 = 1x3 along W) engine with streamed weights (conv1d_tc.cu): BEV's bird's-eye-view stack
+bool tc_conv1d_supported(const ConvParams& p);
+int tc_conv1d_prepare(const ConvParams& p, const float* w_oi3, int sm_count, TcConvPlan* plan, std::vector<void*>* allocs);
+int tc_conv1d_launch(TcConvPlan& plan, const ConvParams& p, cudaStream_t stream);
 // stem engine (conv_stem_tc.cu): 3->64 3x3 stride-2 conv on raw u8 frames with the input normalisation folded in
 bool tc_stem_supported(const ConvParams& p, int ksize, int stride);
 int tc_stem_prepare(const ConvParams& p, const float* w_oihw, int sm_count, bool out_final, TcConvPlan* plan,

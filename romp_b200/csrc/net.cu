@@ -90,9 +90,7 @@ static int fill_params(b200romp_net* net, const Op& op, int batch, ConvParams* o
   p.w = op.d_w_simt; p.bias = op.d_bias;
   p.B = batch;
   p.Hin = ti.H; p.Win = ti.W; p.in_C = ti.C; p.in_c_off = d.in_c_off; p.cin = d.cin;
-  const int kh = d.ksize == 13 ? 1 : d.ksize, kw = d.ksize == 13 ? 3 : d.ksize;   // 13 = Conv1d 1x3
-  p.Hout = (ti.H + 2 * (kh / 2) - kh) / d.stride + 1;
-  p.Wout = (ti.W + 2 * (kw / 2) - kw) / d.stride + 1;
+  conv_out_hw(d.ksize, d.stride, ti.H, ti.W, &p.Hout, &p.Wout);   // 13 = Conv1d 1x3, 42 = ConvTranspose2d(4,2,1)
   p.out_C = to.C; p.out_c_off = d.out_c_off; p.cout = d.cout; p.coutPad = op.coutPad;
   p.up = d.upsample;
   if (d.res >= 0) {
@@ -115,7 +113,8 @@ static int validate_desc(const std::vector<Tensor>& T, const b200romp_conv_desc&
   const int res_c_off = d.res_c_off;
   auto ok_id = [&](int id) { return id >= 0 && id < (int)T.size(); };
   B2R_REQUIRE(ok_id(d.in) && ok_id(d.out) && (d.res == -1 || ok_id(d.res)), "conv: bad tensor id");
-  B2R_REQUIRE((d.ksize == 1 || d.ksize == 3 || (d.ksize == 13 && d.stride == 1 && d.upsample == 1)) && (d.stride == 1 || d.stride == 2),
+  B2R_REQUIRE((d.ksize == 1 || d.ksize == 3 || d.ksize == 7 || (d.ksize == 13 && d.stride == 1 && d.upsample == 1) ||
+               (d.ksize == 42 && d.stride == 2 && d.upsample == 1)) && (d.stride == 1 || d.stride == 2),
               "conv: ksize/stride unsupported");
   B2R_REQUIRE(d.upsample == 1 || d.upsample == 2 || d.upsample == 4 || d.upsample == 8, "conv: upsample must be 1,2,4,8");
   const Tensor& ti = T[d.in];
@@ -123,11 +122,11 @@ static int validate_desc(const std::vector<Tensor>& T, const b200romp_conv_desc&
   B2R_REQUIRE(!ti.nchw, "conv: NCHW inputs unsupported");
   B2R_REQUIRE(d.cin > 0 && d.in_c_off >= 0 && d.in_c_off + d.cin <= ti.C, "conv: input channel slice out of range");
   B2R_REQUIRE(d.cout > 0 && d.out_c_off >= 0 && d.out_c_off + d.cout <= to.C, "conv: output channel slice out of range");
-  const int kh = d.ksize == 13 ? 1 : d.ksize, kw = d.ksize == 13 ? 3 : d.ksize;
-  const int Ho = (ti.H + 2 * (kh / 2) - kh) / d.stride + 1, Wo = (ti.W + 2 * (kw / 2) - kw) / d.stride + 1;
+  int Ho, Wo;
+  conv_out_hw(d.ksize, d.stride, ti.H, ti.W, &Ho, &Wo);
   B2R_REQUIRE(Ho * d.upsample == to.H && Wo * d.upsample == to.W, "conv: output tensor is %dx%d, op produces %dx%d",
               to.H, to.W, Ho * d.upsample, Wo * d.upsample);
-  B2R_REQUIRE(ti.dtype != B200ROMP_U8 || d.input_norm, "conv: u8 input requires input_norm");
+  B2R_REQUIRE(ti.dtype != B200ROMP_U8 || d.input_norm || d.ksize == 7, "conv: u8 input requires input_norm (or the 7x7 stem)");
   B2R_REQUIRE(to.dtype != B200ROMP_U8, "conv: u8 output unsupported");
   B2R_REQUIRE(!to.nchw || to.dtype == B200ROMP_F32, "conv: NCHW output must be fp32");
   if (d.res >= 0) {
@@ -211,7 +210,7 @@ int b200romp_net_add_conv(b200romp_net* net, const b200romp_conv_desc* desc, con
   if (rc) return rc;
   Op op;
   op.d = *desc;
-  const size_t nw = (size_t)desc->cout * desc->cin * (desc->ksize == 13 ? 3 : desc->ksize * desc->ksize);
+  const size_t nw = (size_t)desc->cout * desc->cin * conv_taps(desc->ksize);
   op.w_host.assign(weight, weight + nw);
   op.b_host.assign(desc->cout, 0.f);
   if (bias) op.b_host.assign(bias, bias + desc->cout);
@@ -246,6 +245,23 @@ int b200romp_net_add_sum(b200romp_net* net, const b200romp_sum_desc* desc) {
   return (int)net->ops.size() - 1;
 }
 
+int b200romp_net_add_maxpool(b200romp_net* net, int in, int out) {
+  B2R_REQUIRE(net && !net->finalized, "add_maxpool: net is null or finalized");
+  const int nT = (int)net->tensors.size();
+  B2R_REQUIRE(in >= 0 && in < nT && out >= 0 && out < nT, "add_maxpool: tensor id out of range");
+  const Tensor& ti = net->tensors[in];
+  const Tensor& to = net->tensors[out];
+  B2R_REQUIRE(!ti.nchw && !to.nchw && ti.dtype == to.dtype && ti.dtype != B200ROMP_U8 && ti.C == to.C, "add_maxpool: NHWC bf16/fp32 tensors of equal C");
+  B2R_REQUIRE(to.H == (ti.H + 2 - 3) / 2 + 1 && to.W == (ti.W + 2 - 3) / 2 + 1, "add_maxpool: output must be %dx%d", (ti.H - 1) / 2 + 1, (ti.W - 1) / 2 + 1);
+  Op op;
+  op.kind = 2;
+  memset(&op.d, 0, sizeof(op.d));
+  memset(&op.sum, 0, sizeof(op.sum));
+  op.d.in = in; op.d.out = out; op.d.res = -1;
+  net->ops.push_back(std::move(op));
+  return (int)net->ops.size() - 1;
+}
+
 static int fill_sum_params(b200romp_net* net, const Op& op, int batch, SumParams* out) {
   SumParams p;
   memset(&p, 0, sizeof(p));
@@ -271,22 +287,31 @@ static int enqueue_op(b200romp_net* net, Op& op, int batch, cudaStream_t stream)
     int rc = fill_sum_params(net, op, batch, &sp);
     return rc ? rc : launch_fuse_sum(sp, stream);
   }
+  if (op.kind == 2) {
+    const Tensor& ti = net->tensors[op.d.in];
+    const Tensor& to = net->tensors[op.d.out];
+    B2R_REQUIRE(ti.ptr && to.ptr, "maxpool op: unbound tensor");
+    return launch_maxpool3x3s2(ti.ptr, to.ptr, ti.dtype, batch, ti.H, ti.W, ti.C, stream);
+  }
   ConvParams p;
   int rc = fill_params(net, op, batch, &p);
   if (rc) return rc;
-  if (op.engine == B200ROMP_ENGINE_TCGEN05) return tc_conv_launch(op.tc, p, stream);
+  if (op.d.ksize == 7) return launch_conv_generic(p, 7, op.d.stride, stream);
+  if (op.d.ksize == 42) return launch_deconv4x4s2(p, stream);
+  if (op.engine == B200ROMP_ENGINE_TCGEN05) return op.tc.kind == 13 ? tc_conv1d_launch(op.tc, p, stream) : tc_conv_launch(op.tc, p, stream);
   return launch_conv_simt(p, op.d.ksize, op.d.stride, stream);
 }
 
 static int upload_simt_weights(b200romp_net* net, Op& op) {
   const b200romp_conv_desc& d = op.d;
-  const int taps = d.ksize == 13 ? 3 : d.ksize * d.ksize;
+  const int taps = conv_taps(d.ksize);
   op.coutPad = (d.cout + 63) / 64 * 64;
   std::vector<float> packed((size_t)taps * d.cin * op.coutPad, 0.f);
   for (int co = 0; co < d.cout; ++co)
     for (int ci = 0; ci < d.cin; ++ci)
-      for (int t = 0; t < taps; ++t)
-        packed[((size_t)t * d.cin + ci) * op.coutPad + co] = op.w_host[((size_t)co * d.cin + ci) * taps + t];
+      for (int t = 0; t < taps; ++t)   // conv: OIHW; ConvTranspose2d (code 42): PyTorch's [cin][cout][4][4]
+        packed[((size_t)t * d.cin + ci) * op.coutPad + co] =
+            d.ksize == 42 ? op.w_host[((size_t)ci * d.cout + co) * taps + t] : op.w_host[((size_t)co * d.cin + ci) * taps + t];
   std::vector<float> bias(op.coutPad, 0.f);
   std::copy(op.b_host.begin(), op.b_host.end(), bias.begin());
   B2R_CUDA_OK(cudaMalloc(&op.d_w_simt, packed.size() * sizeof(float)));
@@ -365,13 +390,14 @@ int b200romp_net_finalize(b200romp_net* net, int max_batch) {
   // ---- engine resolution + weight upload
   for (int i = 0; i < nO; ++i) {
     Op& op = net->ops[i];
-    if (op.kind == 1) continue;
+    if (op.kind == 1 || op.kind == 2) continue;
     int rc = upload_simt_weights(net, op);
     if (rc) return rc;
     op.engine = B200ROMP_ENGINE_SIMT;
     const Tensor& ti = net->tensors[op.d.in];
     const Tensor& to = net->tensors[op.d.out];
     const bool stem_like = ti.dtype == B200ROMP_U8 && op.d.cin == 3 && op.d.ksize == 3 && op.d.stride == 2;
+    if (op.d.ksize == 7 || op.d.ksize == 42) { op.w_host.clear(); op.w_host.shrink_to_fit(); continue; }   // CUDA-core kernels of resnet_ops.cu
     const bool want_tf32 = op.d.engine == B200ROMP_ENGINE_TF32 && ti.dtype == B200ROMP_F32;
     const bool want_tc = op.d.engine == B200ROMP_ENGINE_TCGEN05 || want_tf32 ||
                          (op.d.engine == B200ROMP_ENGINE_AUTO && (ti.dtype == B200ROMP_BF16 || stem_like));
@@ -385,11 +411,12 @@ int b200romp_net_finalize(b200romp_net* net, int max_batch) {
         net->tensors[op.d.out].ptr = reinterpret_cast<void*>(16);
         ext_out_unbound = true;
       }
-      if (stem_like && ti.external && ti.ptr == nullptr) {
+      const bool conv1d = op.d.ksize == 13;
+      if ((stem_like || conv1d) && ti.external && ti.ptr == nullptr) {
         net->tensors[op.d.in].ptr = reinterpret_cast<void*>(16);
         ext_in_unbound = true;
       }
-      const bool params_ok = (!ti.external || stem_like) && fill_params(net, op, max_batch, &p) == B200ROMP_OK;
+      const bool params_ok = (!ti.external || stem_like || conv1d) && fill_params(net, op, max_batch, &p) == B200ROMP_OK;
       if (ext_out_unbound) net->tensors[op.d.out].ptr = nullptr;
       if (ext_in_unbound) net->tensors[op.d.in].ptr = nullptr;
       const bool ptrs_final = !to.external && (op.d.res < 0 || !net->tensors[op.d.res].external);
@@ -397,7 +424,12 @@ int b200romp_net_finalize(b200romp_net* net, int max_batch) {
         rc = tc_stem_prepare(p, op.w_host.data(), net->sm_count, ptrs_final, &op.tc, &net->device_allocs);
         if (rc == B200ROMP_OK) op.engine = B200ROMP_ENGINE_TCGEN05;
         else if (op.d.engine == B200ROMP_ENGINE_TCGEN05) return rc;
-      } else if (params_ok && !stem_like && (ti.dtype != B200ROMP_F32 || want_tf32 || op.d.engine == B200ROMP_ENGINE_TCGEN05) &&
+      } else if (params_ok && conv1d && ti.dtype == B200ROMP_BF16 && tc_conv1d_supported(p)) {
+        // (an external input only has a placeholder pointer here: the tensor map is re-encoded at launch)
+        rc = tc_conv1d_prepare(p, op.w_host.data(), net->sm_count, &op.tc, &net->device_allocs);
+        if (rc == B200ROMP_OK) op.engine = B200ROMP_ENGINE_TCGEN05;
+        else if (op.d.engine == B200ROMP_ENGINE_TCGEN05) return rc;
+      } else if (params_ok && !stem_like && !conv1d && (ti.dtype != B200ROMP_F32 || want_tf32 || op.d.engine == B200ROMP_ENGINE_TCGEN05) &&
                  tc_conv_supported(p, op.d.ksize, op.d.stride)) {
         rc = tc_conv_prepare(p, op.d.ksize, op.d.stride, op.w_host.data(), net->sm_count, ptrs_final, &op.tc, &net->device_allocs);
         if (rc == B200ROMP_OK) op.engine = B200ROMP_ENGINE_TCGEN05;
@@ -585,6 +617,11 @@ int b200romp_net_describe(b200romp_net* net, char* buf, int len) {
     const b200romp_conv_desc& d = op.d;
     const Tensor& ti = net->tensors[d.in];
     const Tensor& to = net->tensors[d.out];
+    if (op.kind == 2) {
+      snprintf(line, sizeof(line), "op%03zu maxpool 3x3 s2 in t%d[%dx%dx%d] out t%d[%dx%dx%d]\n", i, d.in, ti.H, ti.W, ti.C, d.out, to.H, to.W, to.C);
+      s += line;
+      continue;
+    }
     if (op.kind == 1) {
       int n = snprintf(line, sizeof(line), "op%03zu sum     out t%d[%dx%dx%d] = relu%d( t%d", i, op.sum.out, to.H, to.W, to.C, op.sum.relu, op.sum.base);
       for (int k = 0; k < op.sum.n_terms; ++k) n += snprintf(line + n, sizeof(line) - n, " + up%d(t%d)", op.sum.up[k], op.sum.term[k]);
@@ -624,9 +661,9 @@ int b200romp_conv2d(const b200romp_conv_desc* d, const float* weight_host, const
   B2R_CUDA_OK(cudaGetDevice(&dev));
   b200romp_net* net = b200romp_net_create(dev);
   if (!net) return B200ROMP_ECUDA;
-  const int pad = d->ksize / 2;
-  const int Ho = ((in_H + 2 * pad - d->ksize) / d->stride + 1) * d->upsample;
-  const int Wo = ((in_W + 2 * pad - d->ksize) / d->stride + 1) * d->upsample;
+  int Ho, Wo;
+  conv_out_hw(d->ksize, d->stride, in_H, in_W, &Ho, &Wo);   // 13 = Conv1d 1x3, 42 = ConvTranspose2d(4,2,1), 7 = 7x7
+  Ho *= d->upsample; Wo *= d->upsample;
   b200romp_conv_desc dd = *d;
   dd.in = b200romp_net_add_tensor(net, in_H, in_W, in_C, in_dtype, 0, 1);
   dd.out = b200romp_net_add_tensor(net, Ho, Wo, out_C, out_dtype, out_nchw, 1);

@@ -144,6 +144,26 @@ class NetBuilder:
         self._added(_lib.check(self.lib.b200romp_net_add_sum(self.net, C.byref(d)), "add_sum"))
         return out
 
+    def maxpool(self, x, name=None):
+        """MaxPool2d(3, 2, 1) (ResNet-50 stem, romp/lib/models/resnet_50.py:42)."""
+        H, W, Cc, dt = self.shape[x]
+        out = self.tensor((H - 1) // 2 + 1, (W - 1) // 2 + 1, Cc, dt, name=name)
+        self._added(_lib.check(self.lib.b200romp_net_add_maxpool(self.net, x, out), "add_maxpool"))
+        return out
+
+    def deconv(self, x, w, b, relu=True, name=None):
+        """ConvTranspose2d(4, 2, 1) + folded BN (+ReLU); w: PyTorch layout [cin, cout, 4, 4] (resnet_50.py:93-120)."""
+        cin, cout = w.shape[0], w.shape[1]
+        H, W, _, _ = self.shape[x]
+        out = self.tensor(2 * H, 2 * W, cout, None, name=name)
+        d = ConvDesc(x, 0, out, 0, -1, 0, 0, cin, cout, 42, 2, int(relu), 1, 0, -1, _lib.ENGINE_SIMT)
+        w = np.ascontiguousarray(w, dtype=np.float32)
+        bp = np.ascontiguousarray(b, dtype=np.float32)
+        self._added(_lib.check(self.lib.b200romp_net_add_conv(self.net, C.byref(d), w.ctypes.data_as(C.POINTER(C.c_float)),
+                                                              bp.ctypes.data_as(C.POINTER(C.c_float))), "add_conv(deconv)"))
+        self.flops_per_frame += 2 * cin * cout * 4 * (2 * H) * (2 * W)
+        return out
+
     def finalize(self, max_batch):
         _lib.check(self.lib.b200romp_net_finalize(self.net, max_batch), "net_finalize")
 
@@ -241,15 +261,10 @@ def build_backbone(nb: NetBuilder, sd, in_dtype):
     return frames, xs[0]
 
 
-def build_romp(sd, device=0, precision="bf16", in_dtype=U8, max_batch=64, engine=_lib.ENGINE_AUTO):
-    """ROMPv1 (HRNet-32 + 3 heads) as a libb200romp conv graph.
-
-    Returns (builder, io) with io = dict(frames=, center_maps=, params_maps=) external tensor ids.
-    """
-    sd = to_numpy_sd(sd)
-    nb = NetBuilder(device, precision, engine)
-    frames, feat = build_backbone(nb, sd, in_dtype)
-
+def build_romp_head(nb: NetBuilder, sd, feat, feat_c):
+    """ROMPv1 heads (model.py:445-481) on a [B,128,128,feat_c] feature tensor -> (center_maps, params_maps) external tensor ids.
+    The three head-in convs (feat_c+2)->64 (3x3, s2, bias, BN, ReLU) are fused into one feat_c->192 conv; the two constant
+    coord channels (model.py:473) become a per-pixel bias map."""
     def cb(x, conv, bn, **kw):
         w, b = fold_bn(sd, conv, bn)
         return nb.conv(x, w, b, **kw)
@@ -258,16 +273,14 @@ def build_romp(sd, device=0, precision="bf16", in_dtype=U8, max_batch=64, engine
         t = cb(x, q + "conv1", q + "bn1", relu=True, in_c_off=in_c_off)
         return cb(t, q + "conv2", q + "bn2", relu=True, res=x, res_c_off=res_c_off)
 
-    # ---- heads (model.py:445-481).  The three head-in convs 34->64 (3x3, s2, bias, BN, ReLU) are fused into
-    # one 32->192 conv; the two constant coord channels (model.py:473) become a per-pixel bias map.
     order = (3, 1, 2)                 # cam, params, center  -> channel slices 0, 64, 128 of the fused tensor
     ws, bs = zip(*[fold_bn(sd, f"final_layers.{h}.0.0", f"final_layers.{h}.0.1") for h in order])
     w_all, b_all = np.concatenate(ws, 0), np.concatenate(bs, 0)
     with torch.no_grad():
-        cm = F.conv2d(coord_maps(128), torch.from_numpy(w_all[:, 32:34].copy()), None, stride=2, padding=1)[0]
+        cm = F.conv2d(coord_maps(128), torch.from_numpy(w_all[:, feat_c:feat_c + 2].copy()), None, stride=2, padding=1)[0]
     bias_map = (cm + torch.from_numpy(b_all)[:, None, None]).permute(1, 2, 0).contiguous().numpy()   # [64,64,192]
     bias_t = nb.const_tensor(bias_map, name="head_bias_map")
-    hin = nb.conv(feat, np.ascontiguousarray(w_all[:, :32]), None, stride=2, relu=True, res=bias_t, res_broadcast=1,
+    hin = nb.conv(feat, np.ascontiguousarray(w_all[:, :feat_c]), None, stride=2, relu=True, res=bias_t, res_broadcast=1,
                   name="head_in")
     center_maps = nb.tensor(64, 64, 1, F32, nchw=1, external=1, name="center_maps")
     params_maps = nb.tensor(64, 64, 145, F32, nchw=1, external=1, name="params_maps")
@@ -283,8 +296,73 @@ def build_romp(sd, device=0, precision="bf16", in_dtype=U8, max_batch=64, engine
                 nb.conv(y, w, b, out=params_maps, out_c_off=3)
             else:
                 nb.conv(y, w, b, out=center_maps)
+    return center_maps, params_maps
+
+
+def build_romp(sd, device=0, precision="bf16", in_dtype=U8, max_batch=64, engine=_lib.ENGINE_AUTO):
+    """ROMPv1 (HRNet-32 + 3 heads) as a libb200romp conv graph.
+
+    Returns (builder, io) with io = dict(frames=, center_maps=, params_maps=) external tensor ids.
+    """
+    sd = to_numpy_sd(sd)
+    nb = NetBuilder(device, precision, engine)
+    frames, feat = build_backbone(nb, sd, in_dtype)
+    center_maps, params_maps = build_romp_head(nb, sd, feat, 32)
     nb.finalize(max_batch)
     return nb, dict(frames=frames, center_maps=center_maps, params_maps=params_maps)
+
+
+IMAGENET_MEAN = np.array([0.485, 0.456, 0.406], np.float32)
+IMAGENET_STD = np.array([0.229, 0.224, 0.225], np.float32)
+
+
+def build_romp_resnet50(sd, device=0, precision="fp32", in_dtype=F32, max_batch=1, engine=_lib.ENGINE_AUTO):
+    """ROMP with the ResNet-50 backbone (romp/lib/models/resnet_50.py:19-120; BASELINE.json configs[0]) as a libb200romp
+    conv graph: 7x7 s2 stem + MaxPool(3,2,1) + [3,4,6,3] Bottlenecks (stride on the 3x3 conv) + three
+    ConvTranspose2d(4,2,1)+BN+ReLU 2048->256->128->64, then ROMPv1's heads on the 64+2 channels.
+    The input normalisation (x/255 - mean)/std (:32-38) is folded into the stem: weights / (255*std) and - because the
+    reference zero-pads the NORMALISED image - a per-pixel bias map = conv(constant image -mean/std, zero padded)."""
+    sd = to_numpy_sd(sd)
+    nb = NetBuilder(device, precision, engine)
+
+    def cb(x, conv, bn, **kw):
+        w, b = fold_bn(sd, conv, bn)
+        return nb.conv(x, w, b, **kw)
+
+    frames = nb.tensor(512, 512, 3, in_dtype, external=1, name="frames")
+    p = "backbone."
+    w, b = fold_bn(sd, p + "conv1", p + "bn1")                                             # [64,3,7,7], BN folded
+    with torch.no_grad():
+        const_img = torch.from_numpy(-IMAGENET_MEAN / IMAGENET_STD).view(1, 3, 1, 1).expand(1, 3, 512, 512).contiguous()
+        bm = F.conv2d(const_img, torch.from_numpy(w), None, stride=2, padding=3)[0] + torch.from_numpy(b)[:, None, None]
+    bias_t = nb.const_tensor(bm.permute(1, 2, 0).contiguous().numpy(), name="stem_bias_map")   # [256,256,64]
+    w_eff = (w / (255.0 * IMAGENET_STD)[None, :, None, None]).astype(np.float32)
+    x = nb.conv(frames, w_eff, None, stride=2, relu=True, res=bias_t, res_broadcast=1)     # resnet_50.py:40-41,57-59
+    x = nb.maxpool(x)                                                                       # :42,60
+    for li, blocks in enumerate((3, 4, 6, 3), start=1):                                     # :43-46, Bottleneck
+        for bi in range(blocks):
+            q = f"{p}layer{li}.{bi}."
+            stride = 2 if (li > 1 and bi == 0) else 1
+            y = cb(x, q + "conv1", q + "bn1", relu=True)
+            y = cb(y, q + "conv2", q + "bn2", stride=stride, relu=True)
+            res = cb(x, q + "downsample.0", q + "downsample.1", stride=stride) if (q + "downsample.0.weight") in sd else x
+            x = cb(y, q + "conv3", q + "bn3", relu=True, res=res)
+    for i in range(3):                                                                      # deconv_layers, :93-120
+        wd = np.asarray(sd[f"{p}deconv_layers.{3 * i}.weight"], np.float64)                # [cin, cout, 4, 4]
+        bn = f"{p}deconv_layers.{3 * i + 1}"
+        scale = np.asarray(sd[bn + ".weight"], np.float64) / np.sqrt(np.asarray(sd[bn + ".running_var"], np.float64) + BN_EPS)
+        shift = np.asarray(sd[bn + ".bias"], np.float64) - np.asarray(sd[bn + ".running_mean"], np.float64) * scale
+        x = nb.deconv(x, (wd * scale[None, :, None, None]).astype(np.float32), shift.astype(np.float32), relu=True)
+    nb.names["backbone_out"] = x
+    center_maps, params_maps = build_romp_head(nb, sd, x, 64)
+    nb.finalize(max_batch)
+    return nb, dict(frames=frames, center_maps=center_maps, params_maps=params_maps)
+
+
+def bev_feats_channels(precision):
+    """channels of the img_feats tensor between bv_pre_layers and b200romp_bev_bv_input: 16 (bev/model.py:166-175), stored
+    zero-padded to 32 in bf16 mode so that the stack runs on the tcgen05 engine"""
+    return 32 if precision == "bf16" else 16
 
 
 def build_bev(sd, device=0, precision="bf16", in_dtype=U8, max_batch=32, engine=_lib.ENGINE_AUTO):
@@ -315,16 +393,33 @@ def build_bev(sd, device=0, precision="bf16", in_dtype=U8, max_batch=32, engine=
     g1.conv(y, w, b, out=maps_fv)                                                     # center_fv | cam_offset(3)
     fv = g1.tensor(128, 128, 128, None, external=1, name="fv_feats")
     head_block(feat, "param_head.0.0.", out=fv)
-    x = feat
-    for i in (0, 3):                                                                   # bv_pre_layers, :166-175
+    # bv_pre_layers (:166-175): 1x1 32->16, 3x3 16->16, 1x1 16->16.  16 channels do not tile onto the tensor-core engine, so in
+    # bf16 mode the stack runs zero-padded to 32 channels (zero weight rows / columns and zero bias: the padded channels are
+    # relu(0) = 0 and contribute nothing downstream) - exact, and 3 tcgen05 launches instead of 0.84 ms of SIMT per step.
+    cf = bev_feats_channels(precision)
+
+    def padded(i, cin_to):
         w, b = fold_bn(sd, f"bv_pre_layers.{i}", f"bv_pre_layers.{i + 1}")
-        x = g1.conv(x, w, b, relu=True, engine=_lib.ENGINE_SIMT)
-    img_feats = g1.tensor(128, 128, 16, None, external=1, name="img_feats")
-    w, b = fold_bn(sd, "bv_pre_layers.6", "bv_pre_layers.7")
-    g1.conv(x, w, b, relu=True, out=img_feats, engine=_lib.ENGINE_SIMT)
+        if cf == 16:
+            return w, b
+        wp = np.zeros((cf, cin_to) + w.shape[2:], np.float32)
+        wp[:w.shape[0], :w.shape[1]] = w
+        bp = np.zeros(cf, np.float32)
+        bp[:b.shape[0]] = b
+        return wp, bp
+
+    eng = _lib.ENGINE_SIMT if cf == 16 else None
+    x = feat
+    w, b = padded(0, 32)
+    x = g1.conv(x, w, b, relu=True, engine=eng)
+    w, b = padded(3, cf)
+    x = g1.conv(x, w, b, relu=True, engine=eng)
+    img_feats = g1.tensor(128, 128, cf, None, external=1, name="img_feats")
+    w, b = padded(6, cf)
+    g1.conv(x, w, b, relu=True, out=img_feats, engine=eng)
     g1.finalize(max_batch)
 
-    g2 = NetBuilder(device, precision, _lib.ENGINE_SIMT)
+    g2 = NetBuilder(device, precision, _lib.ENGINE_AUTO if precision == "bf16" else _lib.ENGINE_SIMT)   # bf16: tcgen05 Conv1d engine (conv1d_tc.cu)
     bv_in = g2.tensor(1, 128, 2560, None, external=1, name="bv_in")
     y = bv_in
     bv_out = g2.tensor(1, 128, 128, None, external=1, name="bv_out")

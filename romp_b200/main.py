@@ -56,6 +56,9 @@ def romp_settings(input_args=sys.argv[1:]):
                         help="conv arithmetic: bf16 tensor cores (fast), tf32 tensor cores on fp32 tensors (the reference's "
                              "default GPU arithmetic, cudnn.allow_tf32) or fp32 CUDA cores (strict parity)")
     parser.add_argument("--max_batch", type=int, default=64, help="largest batch forward_batch will be given")
+    parser.add_argument("--backbone", type=str, default="hrnet32", choices=["hrnet32", "resnet50"],
+                        help="hrnet32 = simple_romp's ROMPv1 (model.py); resnet50 = the training package's ResNet-50 variant "
+                             "(romp/lib/models/resnet_50.py; BASELINE cfg1), state dict with the same head keys")
     parser.add_argument("--cam_trans", type=str, default="lsq", choices=["lsq", "pnp"],
                         help="cam_trans estimator: lsq = closed-form least squares on the GPU (the reference's fallback, "
                              "utils.py:347-389); pnp = the reference's default cv2.solvePnPRansac per person on the host")
@@ -236,8 +239,8 @@ class ROMP(torch.nn.Module):
     # ------------------------------------------------------------------------------------------
     def _net(self, in_dtype):
         if in_dtype not in self._nets:
-            self._nets[in_dtype] = graph.build_romp(self._state_dict, self.device_index, self.precision, in_dtype,
-                                                    self.max_batch)
+            build = graph.build_romp_resnet50 if getattr(self.settings, "backbone", "hrnet32") == "resnet50" else graph.build_romp
+            self._nets[in_dtype] = build(self._state_dict, self.device_index, self.precision, in_dtype, self.max_batch)
         return self._nets[in_dtype]
 
     def _alloc(self, B):

@@ -14,8 +14,12 @@ def conv2d(x_nhwc, w, b=None, *, stride=1, relu=False, res=None, up=1, out_dtype
     """b200romp_conv2d on torch CUDA tensors; x [B,H,W,C] (f32/bf16/u8), w OIHW fp32 numpy."""
     lib = _lib.load()
     B, H, W, Cin_total = x_nhwc.shape
-    cout, cin_w, k, _ = w.shape
-    Ho, Wo = ((H + 2 * (k // 2) - k) // stride + 1) * up, ((W + 2 * (k // 2) - k) // stride + 1) * up
+    if w.ndim == 3:                                   # Conv1d along W: [O, I, 3] -> ksize code 13 (1x3)
+        cout, cin_w, _ = w.shape
+        k, Ho, Wo = 13, H * up, W * up
+    else:
+        cout, cin_w, k, _ = w.shape
+        Ho, Wo = ((H + 2 * (k // 2) - k) // stride + 1) * up, ((W + 2 * (k // 2) - k) // stride + 1) * up
     in_dt = {torch.float32: F32, torch.bfloat16: BF16, torch.uint8: U8}[x_nhwc.dtype]
     shape = (B, cout, Ho, Wo) if out_nchw else (B, Ho, Wo, cout)
     out = torch.empty(shape, dtype=TD[out_dtype], device=x_nhwc.device)
@@ -41,8 +45,12 @@ def conv_ref(x_nhwc_f32, w, b=None, *, stride=1, relu=False, res=None, up=1, inp
     if input_norm:
         x = (x / 255.0) * 2.0 - 1.0
     wt = torch.from_numpy(np.asarray(w, np.float32))
-    y = F.conv2d(x, wt, None if b is None else torch.from_numpy(np.asarray(b, np.float32)), stride=stride,
-                 padding=w.shape[-1] // 2)
+    if wt.ndim == 3:                                  # Conv1d along W
+        wt = wt[:, :, None, :]
+        y = F.conv2d(x, wt, None if b is None else torch.from_numpy(np.asarray(b, np.float32)), stride=1, padding=(0, 1))
+    else:
+        y = F.conv2d(x, wt, None if b is None else torch.from_numpy(np.asarray(b, np.float32)), stride=stride,
+                     padding=w.shape[-1] // 2)
     if up > 1:
         y = F.interpolate(y, scale_factor=up, mode="nearest")
     if res is not None:

@@ -82,3 +82,18 @@ def test_tcgen05_stem_u8(B, H, W):
     ref = conv_ref(x, w_eff, b, stride=2, relu=True, input_norm=1)
     tol = 3e-4 + (2.0 ** -8) * ref.abs()
     assert not ((got - ref).abs() > tol).any(), f"max err {(got - ref).abs().max():.3e}"
+
+
+@pytest.mark.parametrize("cin,cout,B,out_bf16", [(2560, 512, 3, 1), (512, 512, 32, 1), (512, 128, 2, 0), (128, 128, 5, 1)])
+def test_tcgen05_conv1d_streamed_weights(cin, cout, B, out_bf16):
+    """BEV's bird's-eye Conv1d stack (bev/model.py:24-45,179-182) on the streamed-weight tcgen05 engine (conv1d_tc.cu):
+    [B,1,128,C] bf16, k = 3 along W, against torch conv on the same bf16-rounded operands."""
+    rs = np.random.RandomState(cin + cout)
+    x = torch.from_numpy(rs.normal(0, 1, (B, 1, 128, cin)).astype(np.float32)).cuda().bfloat16()
+    w = torch.from_numpy(rs.normal(0, 1 / np.sqrt(cin * 3), (cout, cin, 3)).astype(np.float32)).bfloat16().float().numpy()
+    b = rs.normal(0, 0.5, cout).astype(np.float32)
+    got = conv2d(x, w, b, relu=True, out_dtype=BF16 if out_bf16 else F32, engine=_lib.ENGINE_TCGEN05).float().cpu()
+    ref = conv_ref(x, w, b, relu=True)
+    tol = 3e-4 + (2.0 ** -8) * ref.abs() if out_bf16 else 3e-4 + 1e-5 * ref.abs()
+    bad = (got - ref).abs() > tol
+    assert not bad.any(), f"{int(bad.sum())} of {bad.numel()} outputs off, max err {(got - ref).abs().max():.3e}"

@@ -45,7 +45,7 @@ def test_forward_with_temporal_optimize(largest):
     sd, pack = synth.romp_state_dict(0), synth.smpl_pack(0)
     rs = np.random.RandomState(7)
     base = rs.randint(0, 256, (512, 512, 3)).astype(np.uint8)
-    c, _ = O.romp_maps(sd, base[None, :, :, ::-1])
+    c, _ = O.romp_maps(sd, np.ascontiguousarray(base[None, :, :, ::-1]))
     sd2, _, _ = synth.calibrate_center_head(sd, c.numpy(), max_per_frame=6)
     flags = ["--precision", "fp32", "--max_batch", "1", "-t"] + (["--show_largest"] if largest else [])
     m = ROMP(romp_settings(flags), state_dict=sd2, smpl_pack=pack)
