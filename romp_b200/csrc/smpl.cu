@@ -16,6 +16,8 @@
 //
 // J = J_regressor x (v_t + S b) is evaluated as (J_regressor v_t) + (J_regressor S) b with the two
 // products precomputed in fp64 at create time (linear identity; differences ~1e-7, tolerance 1e-4).
+#include <cuda_fp16.h>
+
 #include <vector>
 
 #include "common.cuh"
@@ -24,8 +26,14 @@ namespace b200romp {
 
 constexpr int kV = 6890;
 constexpr int kJ = 24;
-constexpr int kWsFloats = 512;   // per-person scratch: [0,224) features, [224,512) A[24][12]
-constexpr int kFeatOff = 0, kAOff = 224;
+// per-person scratch record (floats): [0,224) features | [224,512) A[24][12] | [512,848) 448 fp16 (hi | lo split of the features,
+// the tensor-core blend's left operand) | [848,1424) skinning operand | [1424, 1424+20736) v_posed written by the blend GEMM, read
+// by the skinning kernel
+constexpr int kBlendCols = 20736;
+constexpr int kSkinOff = 848;            // [848, 1424): skinning operand A' = 12 rows x 96 fp16 ([A_hi | A_hi | A_lo] per transform entry)
+constexpr int kWsHead = 1424;
+constexpr int kWsFloats = kWsHead + kBlendCols;
+constexpr int kFeatOff = 0, kAOff = 224, kAqOff = 512;
 constexpr int kMaxBetas = 16;
 
 struct SmplDev {
@@ -41,7 +49,16 @@ struct SmplDev {
   const int* csr_rowptr;        // [27]
   const int* csr_col;
   const float* csr_val;
+  const __half* blend_q;        // [20736][672] fp16: B' = [B_hi | B_hi | B_lo] per vertex coordinate (smpl_blend_tc.cu)
+  const __half* skin_w;         // [6912][96] fp16: W' = [W_hi | W_lo | W_hi] per vertex, 24 joints padded to 32
+  const float* vt_pad;          // [20736] v_template, zero padded
 };
+
+// smpl_blend_tc.cu
+int smpl_blend_tc_launch(const void* a_rows, int a_row_stride_bytes, int capacity, const void* b_rows, float* v_posed, const float* v_template_pad,
+                         int n, const int* d_count, int sm_count, cudaStream_t stream);
+int smpl_skin_tc_launch(const void* w_rows, const void* ws_base, int a_off_bytes, int vp_off_floats, int row_stride_bytes, int capacity, int n,
+                        const int* d_count, int sm_count, float* verts, cudaStream_t stream);
 
 __device__ __forceinline__ int person_count(int n, const int* d_count) {
   return d_count ? min(n, *d_count) : n;
@@ -94,6 +111,16 @@ __global__ void __launch_bounds__(128) smpl_pose_kernel(SmplDev m, const float* 
     }
   }
   __syncwarp();
+  {
+    // left operand of the tensor-core blend: features split into fp16 hi + lo, laid out [hi(224) | lo(224)]
+    __half* aq = reinterpret_cast<__half*>(w + kAqOff);
+    for (int k = lane; k < 224; k += 32) {
+      const float f = k < m.K ? w[kFeatOff + k] : 0.f;
+      const __half hi = __float2half_rn(f);
+      const __half lo = __float2half_rn(f - __half2float(hi));
+      aq[k] = hi; aq[224 + k] = lo;
+    }
+  }
   // kinematic chain by tree depth (batch_rigid_transform, smpl.py:260-277): G_i = G_parent * [R_i | J_i - J_parent]
   float G[12];
   for (int level = 0; level < 9; ++level) {
@@ -132,6 +159,18 @@ __global__ void __launch_bounds__(128) smpl_pose_kernel(SmplDev m, const float* 
     for (int a = 0; a < 3; ++a) {
       A[a * 4 + 0] = G[a * 4 + 0]; A[a * 4 + 1] = G[a * 4 + 1]; A[a * 4 + 2] = G[a * 4 + 2];
       A[a * 4 + 3] = G[a * 4 + 3] - (G[a * 4 + 0] * Jl[0] + G[a * 4 + 1] * Jl[1] + G[a * 4 + 2] * Jl[2]);
+    }
+  }
+  __syncwarp();
+  {
+    // right operand of the tensor-core skinning: row e (transform entry) = [A_hi[0..31] | A_hi | A_lo] over the joints (24, zero padded)
+    __half* sk = reinterpret_cast<__half*>(w + kSkinOff);
+    for (int i = lane; i < 12 * 32; i += 32) {
+      const int e = i >> 5, j = i & 31;
+      const float a = j < kJ ? w[kAOff + j * 12 + e] : 0.f;
+      const __half hi = __float2half_rn(a);
+      const __half lo = __float2half_rn(a - __half2float(hi));
+      sk[e * 96 + j] = hi; sk[e * 96 + 32 + j] = hi; sk[e * 96 + 64 + j] = lo;
     }
   }
 }
@@ -210,6 +249,55 @@ __global__ void __launch_bounds__(256) smpl_verts_kernel(SmplDev m, int n_host, 
   }
 }
 
+// Skinning on v_posed produced by the tensor-core blend (smpl_blend_tc.cu): T = W x A, vert = T [v_posed;1] (smpl.py:176-186).
+// CTA = 128 vertices x 32 persons (two halves of 16), W row in registers, A broadcast from shared memory; verts written once.
+__global__ void __launch_bounds__(256) smpl_skin_kernel(SmplDev m, int n_host, const int* __restrict__ d_count,
+                                                        const float* __restrict__ ws, float* __restrict__ verts) {
+  __shared__ __align__(16) float s_A[kPT * 288];
+  const int N = person_count(n_host, d_count);
+  const int n0 = blockIdx.y * kPT;
+  if (n0 >= N) return;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < kPT * 288; i += 256) {
+    const int q = i / 288, e = i % 288;
+    s_A[i] = (n0 + q < N) ? ws[(size_t)(n0 + q) * kWsFloats + kAOff + e] : 0.f;
+  }
+  __syncthreads();
+  const int half = tid >> 7;
+  const int v = blockIdx.x * kVT + (tid & 127);
+  if (v >= kV) return;
+  float wj[kJ];
+  {
+    const float4* w4 = reinterpret_cast<const float4*>(m.weights + (size_t)v * kJ);
+#pragma unroll
+    for (int g = 0; g < 6; ++g) {
+      const float4 t = w4[g];
+      wj[g * 4 + 0] = t.x; wj[g * 4 + 1] = t.y; wj[g * 4 + 2] = t.z; wj[g * 4 + 3] = t.w;
+    }
+  }
+#pragma unroll 2
+  for (int q = 0; q < 16; ++q) {
+    const int n = n0 + half * 16 + q;
+    if (n >= N) break;
+    const float* vp = ws + (size_t)n * kWsFloats + kWsHead + 3 * v;
+    const float px = vp[0], py = vp[1], pz = vp[2];
+    const float4* A4 = reinterpret_cast<const float4*>(s_A + (half * 16 + q) * 288);
+    float4 T0 = make_float4(0.f, 0.f, 0.f, 0.f), T1 = T0, T2 = T0;
+#pragma unroll
+    for (int j = 0; j < kJ; ++j) {
+      const float4 a0 = A4[j * 3 + 0], a1 = A4[j * 3 + 1], a2 = A4[j * 3 + 2];
+      const float w = wj[j];
+      T0.x = fmaf(w, a0.x, T0.x); T0.y = fmaf(w, a0.y, T0.y); T0.z = fmaf(w, a0.z, T0.z); T0.w = fmaf(w, a0.w, T0.w);
+      T1.x = fmaf(w, a1.x, T1.x); T1.y = fmaf(w, a1.y, T1.y); T1.z = fmaf(w, a1.z, T1.z); T1.w = fmaf(w, a1.w, T1.w);
+      T2.x = fmaf(w, a2.x, T2.x); T2.y = fmaf(w, a2.y, T2.y); T2.z = fmaf(w, a2.z, T2.z); T2.w = fmaf(w, a2.w, T2.w);
+    }
+    float* o = verts + ((size_t)n * kV + v) * 3;
+    o[0] = T0.x * px + T0.y * py + T0.z * pz + T0.w;
+    o[1] = T1.x * px + T1.y * py + T1.z * pz + T1.w;
+    o[2] = T2.x * px + T2.y * py + T2.z * pz + T2.w;
+  }
+}
+
 __global__ void __launch_bounds__(256) smpl_joints_kernel(SmplDev m, int n_host, const int* __restrict__ d_count,
                                                           const float* __restrict__ verts, int root_align,
                                                           float* __restrict__ joints, float* __restrict__ ws) {
@@ -266,7 +354,7 @@ __global__ void __launch_bounds__(256) smpl_root_align_kernel(int n_host, const 
 using namespace b200romp;
 
 struct b200romp_smpl {
-  int device = 0;
+  int device = 0, sm_count = 148;
   SmplDev dev;
   std::vector<void*> allocs;
   int smem_verts = 0;
@@ -357,11 +445,33 @@ b200romp_smpl* b200romp_smpl_create(int device, int n_betas, const float* v_temp
     if (eidx[i] < 0 || eidx[i] >= kV) ok = false;
   }
   std::vector<float> vt(v_template, v_template + 3 * kV), w(weights, weights + (size_t)kV * kJ);
+  // tensor-core blend operands: B'[(v,c)][k'] = [B_hi | B_hi | B_lo] (fp16 hi/lo split of the blend matrix), zero padded
+  std::vector<__half> bq((size_t)kBlendCols * 672, __float2half(0.f));
+  std::vector<float> vtp(kBlendCols, 0.f);
+  for (int r = 0; r < 3 * kV; ++r) {
+    vtp[r] = v_template[r];
+    for (int k = 0; k < K; ++k) {
+      const float b = blend[(size_t)k * 3 * kV + r];
+      const __half hi = __float2half_rn(b);
+      const __half lo = __float2half_rn(b - __half2float(hi));
+      bq[(size_t)r * 672 + k] = hi; bq[(size_t)r * 672 + 224 + k] = hi; bq[(size_t)r * 672 + 448 + k] = lo;
+    }
+  }
+  std::vector<__half> wq((size_t)6912 * 96, __float2half(0.f));
+  for (int v = 0; v < kV; ++v)
+    for (int j = 0; j < kJ; ++j) {
+      const float x = weights[(size_t)v * kJ + j];
+      const __half hi = __float2half_rn(x);
+      const __half lo = __float2half_rn(x - __half2float(hi));
+      wq[(size_t)v * 96 + j] = hi; wq[(size_t)v * 96 + 32 + j] = lo; wq[(size_t)v * 96 + 64 + j] = hi;
+    }
+  { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) s->sm_count = prop.multiProcessorCount; }
   SmplDev& d = s->dev;
   d.n_betas = n_betas; d.K = K;
   ok = ok && upload(s, vt, &d.v_template) == 0 && upload(s, blend, &d.blend) == 0 && upload(s, w, &d.weights) == 0 &&
        upload(s, Jt, &d.J_template) == 0 && upload(s, Js, &d.J_shape) == 0 && upload(s, eidx, &d.extra_idx) == 0 &&
-       upload(s, rowptr, &d.csr_rowptr) == 0 && upload(s, cols, &d.csr_col) == 0 && upload(s, vals, &d.csr_val) == 0;
+       upload(s, rowptr, &d.csr_rowptr) == 0 && upload(s, cols, &d.csr_col) == 0 && upload(s, vals, &d.csr_val) == 0 &&
+       upload(s, bq, &d.blend_q) == 0 && upload(s, vtp, &d.vt_pad) == 0 && upload(s, wq, &d.skin_w) == 0;
   s->smem_verts = (224 * kPT + kPT * 288) * (int)sizeof(float);
   ok = ok && cudaFuncSetAttribute(smpl_verts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_verts) == cudaSuccess;
   if (!ok) {
@@ -389,7 +499,22 @@ int b200romp_smpl_forward(b200romp_smpl* s, const float* betas, int betas_stride
   smpl_pose_kernel<<<(n + 3) / 4, 128, 0, stream>>>(s->dev, betas, betas_stride, thetas, n, d_count, workspace, joints);
   B2R_CUDA_OK(cudaGetLastError());
   dim3 grid((kV + kVT - 1) / kVT, (n + kPT - 1) / kPT);
-  smpl_verts_kernel<<<grid, 256, s->smem_verts, stream>>>(s->dev, n, d_count, workspace, verts);
+  static const bool simt_blend = [] { const char* e = getenv("B200ROMP_SMPL_SIMT"); return e && e[0] == '1'; }();
+  if (simt_blend) {       // round-1 formulation: fp32 FFMA blend + skinning in one SIMT kernel (kept for A/B measurements)
+    smpl_verts_kernel<<<grid, 256, s->smem_verts, stream>>>(s->dev, n, d_count, workspace, verts);
+  } else {                // shape + pose blend as a tcgen05 GEMM (3-term fp16 split), then skinning on its v_posed
+    int rc = smpl_blend_tc_launch(reinterpret_cast<const char*>(workspace) + kAqOff * sizeof(float), kWsFloats * (int)sizeof(float), n, s->dev.blend_q,
+                                  workspace + kWsHead, s->dev.vt_pad, n, d_count, s->sm_count, stream);
+    if (rc) return rc;
+    static const bool simt_skin = [] { const char* e = getenv("B200ROMP_SMPL_SKIN_SIMT"); return e && e[0] == '1'; }();
+    if (simt_skin) {      // FFMA skinning on the blend's v_posed (300 FMA per vertex and person; A/B switch)
+      smpl_skin_kernel<<<grid, 256, 0, stream>>>(s->dev, n, d_count, workspace, verts);
+    } else {              // skinning as a tiny-K tcgen05 GEMM (smpl_blend_tc.cu: smpl_skin_tc_kernel)
+      rc = smpl_skin_tc_launch(s->dev.skin_w, workspace, kSkinOff * (int)sizeof(float), kWsHead, kWsFloats * (int)sizeof(float), n, n, d_count,
+                               s->sm_count, verts, stream);
+      if (rc) return rc;
+    }
+  }
   B2R_CUDA_OK(cudaGetLastError());
   smpl_joints_kernel<<<n, 256, 0, stream>>>(s->dev, n, d_count, verts, root_align, joints, workspace);
   B2R_CUDA_OK(cudaGetLastError());

@@ -132,6 +132,7 @@ class ShardGather:
         rb = layout.row_bytes
         self.send = [torch.zeros(1 + self.capacity, rb, dtype=torch.uint8, device=self.device) for _ in range(2)]
         self.recv = [None, None]
+        self._hdr_host = [None, None]
         self.slot = 0
         self.collectives = 0           # all-gathers issued so far (tests / gpu_launches accounting)
 
@@ -156,9 +157,19 @@ class ShardGather:
         self.collectives += 1
         return recv
 
+    def _headers_to_host(self, slot, recv, rows):
+        """enqueue (on the gather stream) the copy of the world x 32-byte headers into this slot's pinned host mirror"""
+        hdr = recv.view(self.world, 1 + rows, self.layout.row_bytes)[:, 0, :HEADER_WORDS * 4].contiguous()
+        if self._hdr_host[slot] is None:
+            t = torch.zeros(self.world, HEADER_WORDS * 4, dtype=torch.uint8)
+            self._hdr_host[slot] = t.pin_memory() if self.cuda else t
+        self._hdr_host[slot].copy_(hdr, non_blocking=True)
+
     def submit(self, fields: dict, count, frame_offset: int, rows_hint: int | None = None):
         """fields: name -> tensor [cap, ...] (device tensors of the ROMP slot, or CPU tensors under gloo);
-        count: python int or int32 device tensor.  Returns a handle for result()."""
+        count: python int or int32 device tensor.  Returns a handle for counts() / result().  Everything (pack kernel, the
+        all-gather, the copy of the gathered headers to pinned host memory) is enqueued on the gather's own stream after
+        the caller's current stream: no host synchronisation, nothing on the legacy default stream."""
         slot, self.slot = self.slot, self.slot ^ 1
         rows = min(self.capacity, max(1, int(self.rows_hint if rows_hint is None else rows_hint)))
         if self.cuda:
@@ -170,6 +181,7 @@ class ShardGather:
                 packed = torch.cuda.Event()
                 packed.record(self.stream)          # from here on the caller may overwrite `fields`
                 recv = self._gather(slot, rows)
+                self._headers_to_host(slot, recv, rows)
                 done = torch.cuda.Event()
                 done.record(self.stream)
             for t in fields.values():
@@ -178,6 +190,7 @@ class ShardGather:
         else:
             pack_rows(self.layout, fields, count, frame_offset, self.send[slot])
             recv, done, packed = self._gather(slot, rows), None, None
+            self._headers_to_host(slot, recv, rows)
         return dict(slot=slot, rows=rows, recv=recv, done=done, packed=packed)
 
     def wait(self, handle, stream=None):
@@ -185,37 +198,52 @@ class ShardGather:
         if handle["done"] is not None:
             (torch.cuda.current_stream() if stream is None else stream).wait_event(handle["done"])
 
-    def result(self, handle, to_numpy=False):
-        """Every rank's persons in global frame order as a dict of tensors on the gather device (or numpy arrays),
-        or None when nobody was detected anywhere.  The one host synchronisation: the gathered headers."""
-        slot, rows, recv = handle["slot"], handle["rows"], handle["recv"]
+    def counts(self, handle):
+        """(person counts, first-frame offsets) of every rank for this step.  The one host wait: the step's gather event;
+        the headers were already copied to pinned host memory on the gather stream.  If some rank held more persons than
+        the rows hint, every rank sees it here and all of them repeat the gather with the exact maximum (collectively
+        decided: the headers are identical on all ranks)."""
+        if "counts" in handle:
+            return handle["counts"], handle["offsets"]
+        slot = handle["slot"]
         if handle["done"] is not None:
             handle["done"].synchronize()
         rb = self.layout.row_bytes
-        per = 1 + rows
-        hdr = recv.view(self.world, per, rb)[:, 0, :HEADER_WORDS * 4].contiguous().view(torch.int32).cpu()
+        hdr = self._hdr_host[slot].view(torch.int32).view(self.world, HEADER_WORDS)
         assert bool((hdr[:, 0] == MAGIC).all()) and bool((hdr[:, 4] == rb).all()), "record layout differs between ranks"
         counts, offsets = hdr[:, 1].tolist(), hdr[:, 2].tolist()
         nmax = max(counts)
         self.rows_hint = min(self.capacity, max(16, int(nmax * 1.25) + 8))      # next step's bound
-        if nmax > rows:
-            # some rank held more persons than the hint: every rank sees the same headers, so all of them repeat the
-            # gather with the exact maximum (the send buffers still hold the full pack)
+        if nmax > handle["rows"]:
             if self.cuda:
                 with torch.cuda.stream(self.stream):
-                    recv = self._gather(slot, nmax)
-                    self.stream.synchronize()
+                    handle["recv"] = self._gather(slot, nmax)
+                self.stream.synchronize()
             else:
-                recv = self._gather(slot, nmax)
-            rows, per = nmax, 1 + nmax
-        if nmax == 0:
+                handle["recv"] = self._gather(slot, nmax)
+            handle["rows"] = nmax
+        handle["counts"], handle["offsets"] = counts, offsets
+        return counts, offsets
+
+    def result(self, handle, to_numpy=False):
+        """Every rank's persons in global frame order as a dict of tensors on the gather device (or numpy arrays), or None
+        when nobody was detected anywhere.  The concatenation runs on the gather stream."""
+        counts, offsets = self.counts(handle)
+        if max(counts) == 0:
             return None
-        v = recv.view(self.world, per, rb)
-        parts = [v[r, 1:1 + c] for r, c in enumerate(counts) if c]
+        rows, recv = handle["rows"], handle["recv"]
+        v = recv.view(self.world, 1 + rows, self.layout.row_bytes)
         offs = torch.cat([torch.full((c,), o, dtype=torch.int64) for c, o in zip(counts, offsets) if c])
-        out = unpack_rows(self.layout, torch.cat(parts, 0), offs)
+        if self.cuda:
+            with torch.cuda.stream(self.stream):
+                out = unpack_rows(self.layout, torch.cat([v[r, 1:1 + c] for r, c in enumerate(counts) if c], 0), offs.to(self.device, non_blocking=True))
+                if to_numpy:
+                    out = {k: t.cpu() for k, t in out.items()}
+            self.stream.synchronize()
+        else:
+            out = unpack_rows(self.layout, torch.cat([v[r, 1:1 + c] for r, c in enumerate(counts) if c], 0), offs)
         if to_numpy:
-            out = {k: t.cpu().numpy() for k, t in out.items()}
+            out = {k: t.numpy() for k, t in out.items()}
         return out
 
 
