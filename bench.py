@@ -306,7 +306,7 @@ def run_ours(args):
                 "h2d_bytes_per_step": int(frames_host.numel()), "d2h_bytes_per_step": d2h,
                 "note": "per rank: H2D of its frames, D2H of its own shard's result dict" +
                         ("; all ranks' records all-gathered on the device every step (%d persons seen by rank 0)" % gathered_persons if world > 1 else "")},
-        "gpu_launches": (n_launch + 2 + 3 + 2 + (1 if world > 1 else 0)) * steps,   # per timed device pass: conv graph, parse, SMPL, projection, pack
+        "gpu_launches": (n_launch + 2 + 4 + 2 + (1 if world > 1 else 0)) * steps,   # per timed device pass: conv graph, parse 2, SMPL 4 (pose, blend GEMM, skinning GEMM, joints), projection 2, pack
         "roofline": {"bound": "tensor", "achieved": net_tflops, "peak": peak, "unit": "TFLOP/s",
                      "frac": net_tflops / peak, "frac_of_sustained_peak": net_tflops / (peaks["bf16"] * (1.0 if args.precision == "bf16" else 0.5)),
                      "traffic": traffic,
@@ -398,9 +398,9 @@ def run_smpl(args, emit_line=True):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "cfg5 SMPL-only, %d persons, betas~N(0,1), thetas~N(0,0.3), synthetic SMPL pack" % n},
         "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
-                     "traffic": None, "peak_source": peaks["src"], "kernel": "smpl_pose + smpl_verts + smpl_joints",
+                     "traffic": None, "peak_source": peaks["src"], "kernel": "smpl_pose + smpl_blend_tc (tcgen05 GEMM) + smpl_skin_tc (tcgen05 GEMM) + smpl_joints",
                      "algorithmic_bytes_per_launch": n * SMPL_BYTES_PER_PERSON},
-        "gpu_launches": 3 * steps}
+        "gpu_launches": 4 * steps}
     del verts, joints, ws
     torch.cuda.empty_cache()
     if emit_line:

@@ -291,7 +291,7 @@ constexpr int kSkChunk = 128 * 64;         // resident W' chunk: 128 vertices x 
 constexpr int kSkBChunk = kSkN * 64;       // streamed A' chunk: 192 rows x 64 B
 constexpr int kSkStage = 3 * kSkBChunk;    // 36,864
 constexpr int kSkStages = 4;
-constexpr int kSkThreads = 192;
+constexpr int kSkThreads = 320;           // warp 0 producer, warp 1 MMA, warps 2-9 epilogue: two groups of four, one accumulator each
 constexpr uint32_t kSkIdesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(kSkN >> 3) << 17) | ((128u >> 4) << 24);
 
 __device__ __forceinline__ void tma_load_3d_plain(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
@@ -381,11 +381,14 @@ smpl_skin_tc_kernel(const __grid_constant__ SkinMaps maps, const float* __restri
     }
   } else {
     // ===================== epilogue: thread = vertex, loops over the tile's 16 persons =====================
+    // two groups of four warps alternate tiles (group g owns accumulator g): while one group waits for / drains its
+    // accumulator, the other group's 48 v_posed loads per thread are in flight
     const int q = warp & 3;
+    const int group = (warp - 2) >> 2;
     const int v = vt * 128 + q * 32 + lane;
     const bool v_ok = v < 6890;
-    int it = 0;
-    for (int pt = blockIdx.y; pt < ptiles; pt += gridDim.y, ++it) {
+    int it = group;
+    for (int pt = blockIdx.y + group * gridDim.y; pt < ptiles; pt += 2 * gridDim.y, it += 2) {
       const int acc = it & 1;
       const int np = min(kSkP, N - pt * kSkP);
       // v_posed of this vertex for all 16 persons: 48 independent loads issued BEFORE the accumulator is awaited (they do not
