@@ -9,6 +9,10 @@
  * Every call enqueues work on the caller's CUDA stream and returns immediately; the caller owns all
  * input/output buffers; the library owns only packed constants and the conv-graph workspace.
  *
+ * Device selection: entry points that take a handle (net, smpl, bev, tracks) make the handle's device current themselves;
+ * the handle-less ones (parse, project, preprocess_bgr, pack_rows, bev_bv_input / parse3d / post, gather_rows) launch on
+ * the CURRENT device - the caller must have made the device that owns the stream and the buffers current.
+ *
  * Return convention: 0 = OK, negative = error (b200romp_last_error() gives the text).  "Nobody
  * detected" is NOT an error: the person count simply comes back as 0 (reference: post_parser.py:138-140).
  * There is no CPU fallback anywhere in this library.

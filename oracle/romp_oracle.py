@@ -389,7 +389,10 @@ def orth_project(X, cam, keep_dim=False):
 
 
 def to_org_image(kps, offsets):
-    """convert_proejection_from_input_to_orgimg, post_parser.py:81-88 (returns a new tensor)."""
+    """convert_proejection_from_input_to_orgimg, post_parser.py:81-88.  Returns a NEW tensor; the reference mutates its
+    argument in place, so that in its output dict `pj2d` aliases `pj2d_org` - BEV's duplicate-suppression filter
+    (bev/post_parser.py:167-198) is called with that aliased tensor, i.e. with original-image pixels; csrc/bev.cu and
+    oracle/bev_oracle.py honour this by feeding the filter `pj2d_org`."""
     top, bottom, left, right, h, w = [float(v) for v in offsets]
     size = max(h, w)
     out = _t(kps).clone()

@@ -552,6 +552,7 @@ int b200romp_bev_bv_input(const float* maps_fv, const void* img_feats, int feats
 int b200romp_bev_center3d(b200romp_bev* h, const float* maps_fv, const void* bv_out, int bv_dtype, int batch, float* tmp,
                           float* center3d, b200romp_stream stream) {
   B2R_REQUIRE(h && maps_fv && bv_out && tmp && center3d && batch > 0, "bev_center3d: bad arguments");
+  B2R_CUDA_OK(cudaSetDevice(h->device));
   static const bool two_pass = [] { const char* e = getenv("B200ROMP_BEV_CENTER3D_2PASS"); return e && e[0] == '1'; }();
   if (two_pass) {                      // round-1 formulation (one thread per voxel, intermediate in `tmp`): kept for A/B checks
     const size_t n = (size_t)batch * kVol;
@@ -595,6 +596,7 @@ int b200romp_bev_regress(b200romp_bev* h, const float* maps_fv, const void* bv_o
                          long long* cam_czyx, float* cam, float* thetas, float* betas, float* cam_trans, b200romp_stream stream_) {
   B2R_REQUIRE(h && maps_fv && bv_out && fv_feats && d_count && batch_ids && czyx && params_pred && cam_czyx && cam && thetas &&
                   betas && cam_trans && capacity > 0, "bev_regress: bad arguments");
+  B2R_CUDA_OK(cudaSetDevice(h->device));
   cudaStream_t stream = (cudaStream_t)stream_;
   bev_regress_kernel<<<capacity, 256, 0, stream>>>(h->dev, maps_fv, bv_out, bv_dtype, fv_feats, fv_dtype, d_count, batch_ids, czyx,
                                                    params_pred, cam_czyx);

@@ -12,7 +12,7 @@
 // Kernel (CTA pairs, cta_group::2, one UMMA = 256 persons x 256 coordinates x 16):
 //   * the pair owns a 256-person tile: each CTA keeps ITS 128 persons' A' rows resident in shared memory (112 KB, 14 chunks of
 //     32 halfs, SWIZZLE_64B) and walks the 81 coordinate tiles of 256 (a slice of them when there are fewer person tiles than SM pairs);
-//   * B' is streamed: per (coordinate tile, chunk) each CTA TMA-loads its 128 of the 256 rows (8 KB) into a 10-stage ring; both
+//   * B' is streamed: per (coordinate tile, chunk) each CTA TMA-loads its 128 of the 256 rows (8 KB) into a 6-stage ring; both
 //     loads complete on the leader's barrier (conv_tc_2cta.cu protocol); 2 MMAs per chunk, 42 per tile, N = 256 = full rate;
 //   * D: 2 accumulators x 256 fp32 columns in TMEM; each CTA's 4 epilogue warps drain their 32 persons x 256 columns in
 //     chunks of 32 columns: + v_template, staged in shared memory (128 B rows, SWIZZLE_128B), one TMA store per chunk into the
@@ -33,9 +33,9 @@ constexpr int kBlColTiles = kBlCols / 256;
 constexpr int kBlAChunk = 128 * 64;       // one resident A' chunk: 128 persons x 64 B
 constexpr int kBlABytes = kBlAChunks * kBlAChunk;         // 114,688
 constexpr int kBlBStage = 128 * 64;       // this CTA's 128 rows of one B' chunk
-constexpr int kBlStages = 10;             // 8 KB each: ~1 us of TMA latency at 2 MMAs (256 clk) per chunk needs a deep ring
+constexpr int kBlStages = 6;              // 8 KB each: ~1 us of TMA latency at 2 MMAs (256 clk) per chunk needs a deep ring
 constexpr int kBlStgBytes = 32 * 128;     // epilogue staging: 32 persons x 32 fp32 columns per warp buffer
-constexpr int kBlThreads = 192;           // warp 0 producer, warp 1 MMA, warps 2-5 epilogue
+constexpr int kBlThreads = 320;           // warp 0 producer, warp 1 MMA, warps 2-9 epilogue: two groups of four, one accumulator each
 constexpr uint32_t kBlIdesc = (1u << 4) | (0u << 7) | (0u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);   // F32 acc, F16 x F16, N 256, M 256
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
@@ -68,8 +68,8 @@ smpl_blend_tc_kernel(const __grid_constant__ BlendMaps maps, const float* __rest
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                                          // 21 x [128 persons x 64 B]
   uint8_t* sB = sA + kBlABytes;                                // kBlStages x [128 rows x 64 B]
-  uint8_t* sStg = sB + kBlStages * kBlBStage;                  // 4 warps x 2 buffers x 4 KB
-  uint64_t* full = reinterpret_cast<uint64_t*>(sStg + 4 * 2 * kBlStgBytes);
+  uint8_t* sStg = sB + kBlStages * kBlBStage;                  // 8 warps x 2 buffers x 4 KB
+  uint64_t* full = reinterpret_cast<uint64_t*>(sStg + 8 * 2 * kBlStgBytes);
   uint64_t* empty = full + kBlStages;
   uint64_t* a_full = empty + kBlStages;      // this CTA's A' tile landed
   uint64_t* a_peer = a_full + 1;             // (leader) the peer's A' tile landed
@@ -163,13 +163,15 @@ smpl_blend_tc_kernel(const __grid_constant__ BlendMaps maps, const float* __rest
     }
   } else {
     // ===================== epilogue: warp q drains persons [32q, 32q+32) of this CTA, 32 columns at a time =====================
-    const int q = warp & 3;
-    uint8_t* stg0 = sStg + q * 2 * kBlStgBytes;
+    // two groups of four warps; group g drains accumulator g (tiles it = g, g + 2, ... of this pair's sequence)
+    const int q = warp & 3, group = (warp - 2) >> 2;
+    uint8_t* stg0 = sStg + (warp - 2) * 2 * kBlStgBytes;
     int it = 0, buf = 0;
     for (int pt = pair; pt < person_tiles; pt += npairs) {
       const int prow = (pt / col_splits) * 256 + (int)rank * 128 + q * 32;
       const int j0 = (pt % col_splits) * cols_per, j1 = min(kBlColTiles, j0 + cols_per);
       for (int j = j0; j < j1; ++j, ++it) {
+        if ((it & 1) != group) continue;
         const int acc = it & 1;
         mbar_wait(&tmem_full[acc], (it >> 1) & 1);
         tc_fence_after();
@@ -214,7 +216,7 @@ smpl_blend_tc_kernel(const __grid_constant__ BlendMaps maps, const float* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
-constexpr int kBlendSmem = kBlABytes + kBlStages * kBlBStage + 4 * 2 * kBlStgBytes + 256 + 1024;
+constexpr int kBlendSmem = kBlABytes + kBlStages * kBlBStage + 8 * 2 * kBlStgBytes + 256 + 1024;
 
 // a_rows (fp16 [cap] rows of 672) and v_posed (fp32 [cap] rows of 20736) both live inside the per-person scratch record of smpl.cu:
 // consecutive persons are `row_stride_bytes` apart in BOTH tensors

@@ -112,7 +112,9 @@ def test_nobody_returns_none_and_single_image_forward(params):
     assert np.array_equal(out["center_preds"], ref["center_preds"].numpy())
     v, j = O.smpl_forward(params[1], ref["smpl_betas"], ref["smpl_thetas"])
     pr = O.project_outputs(j, None, ref["cam"], pad)
-    assert np.abs(out["pj2d_org"] - pr["pj2d_org"].numpy()).max() < 0.5   # pixels in the 400x300 original image
+    err_px = np.abs(out["pj2d_org"] - pr["pj2d_org"].numpy()).max()
+    print(f"pj2d_org max err {err_px:.2e} px")
+    assert err_px < 0.02                                                   # pixels in the 400x300 original image (fp32 engine)
 
 
 def test_forward_batches_pipeline_equals_forward_batch(params):
