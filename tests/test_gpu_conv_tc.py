@@ -97,3 +97,19 @@ def test_tcgen05_conv1d_streamed_weights(cin, cout, B, out_bf16):
     tol = 3e-4 + (2.0 ** -8) * ref.abs() if out_bf16 else 3e-4 + 1e-5 * ref.abs()
     bad = (got - ref).abs() > tol
     assert not bad.any(), f"{int(bad.sum())} of {bad.numel()} outputs off, max err {(got - ref).abs().max():.3e}"
+
+
+@pytest.mark.parametrize("k,cin,cout,hw", [(3, 32, 32, 32), (3, 64, 64, 32), (3, 128, 128, 16), (3, 256, 256, 16), (1, 64, 256, 32)])
+def test_bf16_rounding_error_of_one_layer_is_bounded(k, cin, cout, hw):
+    """What the bf16 engine costs per layer (the cases above compare on identical bf16-rounded operands and cannot see it):
+    conv(bf16(x), bf16(w)) stored as bf16 against the fp32 conv of the UNROUNDED operands.  Each operand carries a relative
+    rounding error <= 2^-9, the output one more: the relative L2 error of a layer must stay below 3 x 2^-9 (measured
+    ~3e-3); a kernel that accumulated in bf16, or dropped K terms, would exceed it."""
+    rs = np.random.RandomState(k * 1000 + cin)
+    x = rs.normal(0, 1, (2, hw, hw, cin)).astype(np.float32)
+    w = rs.normal(0, 1 / np.sqrt(cin * k * k), (cout, cin, k, k)).astype(np.float32)
+    got = conv2d(torch.from_numpy(x).cuda().bfloat16(), w, None, out_dtype=BF16, engine=_lib.ENGINE_TCGEN05).float().cpu()
+    ref = conv_ref(torch.from_numpy(x), w)
+    rel = float((got - ref).norm() / ref.norm())
+    print(f"k{k} {cin}->{cout}: relative L2 error of the bf16 layer {rel:.2e}")
+    assert rel < 3 * 2.0 ** -9
