@@ -268,8 +268,9 @@ int tc_pack_weights(const float* w_oihw, int cin, int cout, int taps, int nt, vo
 }
 
 std::string TcConvPlan::describe() const {
-  char buf[96];
-  snprintf(buf, sizeof(buf), " [tc%s k%d v%d nt%d grid %dx%d smem %d stages %d epi%d]", eb == 4 ? "-tf32" : "", kind / 10, kind % 10, nt, grid_x, grid_y, smem_bytes, stages, tma_epi);
+  char buf[128];
+  snprintf(buf, sizeof(buf), " [tc%s k%d v%d nt%d grid %dx%d smem %d stages %d epi%d%s]", eb == 4 ? "-tf32" : "", kind / 10, kind % 10, nt, grid_x, grid_y, smem_bytes, stages, tma_epi,
+           kmask != 0xFFFFFFFFu ? " pixel-pairs" : "");
   return buf;
 }
 

@@ -19,6 +19,9 @@ struct TcConvPlan {
   alignas(64) unsigned char tmap_s2[4][128];  // stride-2: one map per input parity (ph,pw)
   alignas(64) unsigned char tmap_epi[2][128]; // TMA epilogue: output / residual tensor (box NT x 8 x 4 x 1)
   int tma_epi = 0;              // bit 0: output through a TMA store, bit 1: residual through a TMA load
+  // CTA-pair engine: bit (tap * 2 + half) = 0 skips the MMAs of that channel half of that tap (all-zero weights of a
+  // pixel-pair folded conv, see net.cu fold_pixel_pairs)
+  unsigned kmask = 0xFFFFFFFFu;
   const void* encoded_in = nullptr;   // conv1d engine: input pointer / batch the tensor map was encoded for (external inputs)
   int encoded_batch = 0;
   std::string describe() const;

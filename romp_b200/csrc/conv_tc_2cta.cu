@@ -43,7 +43,8 @@ struct Tc2Cfg {
 template <int CIN, int NT, int EB>
 __global__ void __launch_bounds__(tc_threads(EB), 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcEpiMaps epi_maps, const ConvParams p,
-                const uint8_t* __restrict__ wpack, int tiles_x, int tiles_y, int num_tiles, int stages, int tma_epi) {
+                const uint8_t* __restrict__ wpack, int tiles_x, int tiles_y, int num_tiles, int stages, int tma_epi,
+                unsigned kmask) {
   using Cfg = Tc2Cfg<CIN, NT, EB>;
   constexpr int kAccStages = Cfg::ACC;
   extern __shared__ uint8_t smem_raw[];
@@ -158,6 +159,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             const uint32_t b_tap = b_base + (uint32_t)((t * Cfg::KCH + c) * Cfg::BTILE);
 #pragma unroll
             for (int k = 0; k < Cfg::KSTEPS; ++k) {
+              // channel half of this K step: which of the two chunks (KCH = 2) or which half of the row (KCH = 1)
+              const int half = Cfg::KCH == 2 ? c : (Cfg::KCH == 1 ? k / (Cfg::KSTEPS / 2) : 0);
+              if (Cfg::KCH <= 2 && !((kmask >> (t * 2 + half)) & 1u)) continue;   // folded conv: this weight block is all zero
               const uint64_t adesc = make_smem_desc(a_tap + k * 32, Cfg::HW_ * Cfg::ROWB, Cfg::LAYOUT);
               const uint64_t bdesc = make_smem_desc(b_tap + k * 32, 8 * Cfg::ROWB, Cfg::LAYOUT);
               umma_any<EB, true>(d_tile, adesc, bdesc, Cfg::IDESC, mma_i > 0 ? 1u : 0u);
@@ -274,7 +278,7 @@ static int tc2_inst(const TcConvPlan& plan, const ConvParams& p, cudaStream_t st
   cfg.attrs = at;
   cfg.numAttrs = pdl ? 2 : 1;
   B2R_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tm, em, p, reinterpret_cast<const uint8_t*>(plan.d_wpack), tiles_x, tiles_y, num_tiles,
-                                 plan.stages, plan.tma_epi));
+                                 plan.stages, plan.tma_epi, plan.kmask));
   return B200ROMP_OK;
 }
 

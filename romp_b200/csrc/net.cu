@@ -48,6 +48,7 @@ struct Op {
   int engine = B200ROMP_ENGINE_SIMT;   // resolved
   TcConvPlan tc;                       // tcgen05 plan (packed weights, tensor maps)
   int lane = 0;                        // concurrency lane inside the captured CUDA graph (b200romp_net_set_lane)
+  int fold = 0;                        // 1 = runs as a pixel-pair folded 64->64 conv on the [H, W/2, 64] view (fold_pixel_pairs)
 };
 
 }  // namespace b200romp
@@ -101,6 +102,10 @@ static int fill_params(b200romp_net* net, const Op& op, int batch, ConvParams* o
   p.relu = d.relu; p.pow_channel = d.pow_channel; p.out_nchw = to.nchw;
   p.in_dtype = ti.dtype; p.out_dtype = to.dtype; p.input_norm = d.input_norm;
   { static const int dbg = getenv("B200ROMP_TC_DEBUG") ? atoi(getenv("B200ROMP_TC_DEBUG")) : 0; p.debug = dbg; }
+  if (op.fold) {   // the same bytes seen as [B, H, W/2, 2C]: two horizontally adjacent pixels form one 64-channel pixel
+    p.Win /= 2; p.Wout /= 2;
+    p.in_C *= 2; p.cin *= 2; p.out_C *= 2; p.cout *= 2; p.res_C *= 2;
+  }
   if (!p.in || !p.out) {
     set_error("op uses an unbound tensor (in=%d out=%d)", d.in, d.out);
     return B200ROMP_ESTATE;
@@ -323,6 +328,53 @@ static int upload_simt_weights(b200romp_net* net, Op& op) {
   return B200ROMP_OK;
 }
 
+// Pixel-pair folding of a 32->32 3x3 stride-1 conv.  With N = Cout = 32 every tcgen05.mma still fetches a
+// full 128-row A tile from shared memory, so the operand fetch (not the tensor pipe) bounds the layer.  Viewing the NHWC
+// tensors as [B, H, W/2, 64] turns the layer into a 64->64 conv whose 3x3 kernel over PAIRS has structured zeros:
+// output pair r = pixels (2r, 2r+1) reads pixels 2r-1 .. 2r+2, i.e. pair r-1 (second pixel only), pair r, pair r+1 (first
+// pixel only).  W2[dx*32+co][h*32+ci][ky][s+1] = W[co][ci][ky][2s+h-dx+1] when that kx is in 0..2, else 0.  The all-zero
+// halves (s=-1,h=0 and s=+1,h=1) are skipped through the plan's kmask: 24 MMAs of N = 64 per 256 pixels instead of 36 of
+// N = 32, 26 % fewer shared-memory operand wavefronts, and the epilogue handles 128-byte rows.
+static bool fold_eligible(const b200romp_net* net, const Op& op) {
+  static const bool off = [] { const char* e = getenv("B200ROMP_TC_NO_FOLD"); return e && e[0] == '1'; }();
+  const b200romp_conv_desc& d = op.d;
+  const Tensor& ti = net->tensors[d.in];
+  const Tensor& to = net->tensors[d.out];
+  if (off || d.ksize != 3 || d.stride != 1 || d.upsample != 1 || d.cin != 32 || d.cout != 32) return false;
+  if (ti.C != 32 || to.C != 32 || d.in_c_off || d.out_c_off || ti.external || to.external) return false;
+  if (ti.dtype != B200ROMP_BF16 || to.dtype != B200ROMP_BF16 || to.nchw || d.pow_channel >= 0 || d.input_norm) return false;
+  if (ti.W % 16 != 0 || ti.H % 16 != 0) return false;
+  if (d.res >= 0) {
+    const Tensor& tr = net->tensors[d.res];
+    if (tr.C != 32 || d.res_c_off || d.res_broadcast || tr.dtype != B200ROMP_BF16 || tr.external) return false;
+  }
+  return true;
+}
+
+static void fold_pixel_pairs(const std::vector<float>& w, const std::vector<float>& b, std::vector<float>* w2, std::vector<float>* b2,
+                             unsigned* kmask) {
+  w2->assign((size_t)64 * 64 * 9, 0.f);
+  for (int dx = 0; dx < 2; ++dx)
+    for (int co = 0; co < 32; ++co)
+      for (int h = 0; h < 2; ++h)
+        for (int ci = 0; ci < 32; ++ci)
+          for (int ky = 0; ky < 3; ++ky)
+            for (int s = -1; s <= 1; ++s) {
+              const int kx = 2 * s + h - dx + 1;
+              if (kx < 0 || kx > 2) continue;
+              (*w2)[(((size_t)(dx * 32 + co) * 64 + h * 32 + ci) * 3 + ky) * 3 + (s + 1)] = w[(((size_t)co * 32 + ci) * 3 + ky) * 3 + kx];
+            }
+  b2->assign(64, 0.f);
+  for (int i = 0; i < 64; ++i) (*b2)[i] = (i % 32) < (int)b.size() ? b[i % 32] : 0.f;
+  unsigned m = 0;
+  for (int t = 0; t < 9; ++t) {
+    const int s = t % 3 - 1;
+    if (s != -1) m |= 1u << (t * 2 + 0);   // first pixel of the pair is used by s = 0, +1
+    if (s != +1) m |= 1u << (t * 2 + 1);   // second pixel by s = -1, 0
+  }
+  *kmask = m;
+}
+
 int b200romp_net_finalize(b200romp_net* net, int max_batch) {
   B2R_REQUIRE(net && !net->finalized && max_batch > 0, "finalize: bad arguments");
   B2R_CUDA_OK(cudaSetDevice(net->device));
@@ -431,7 +483,26 @@ int b200romp_net_finalize(b200romp_net* net, int max_batch) {
         else if (op.d.engine == B200ROMP_ENGINE_TCGEN05) return rc;
       } else if (params_ok && !stem_like && !conv1d && (ti.dtype != B200ROMP_F32 || want_tf32 || op.d.engine == B200ROMP_ENGINE_TCGEN05) &&
                  tc_conv_supported(p, op.d.ksize, op.d.stride)) {
-        rc = tc_conv_prepare(p, op.d.ksize, op.d.stride, op.w_host.data(), net->sm_count, ptrs_final, &op.tc, &net->device_allocs);
+        rc = -1;
+        if (fold_eligible(net, op)) {
+          std::vector<float> w2, b2;
+          unsigned kmask = 0;
+          fold_pixel_pairs(op.w_host, op.b_host, &w2, &b2, &kmask);
+          ConvParams pf;
+          op.fold = 1;
+          TcConvPlan plan;
+          if (fill_params(net, op, max_batch, &pf) == B200ROMP_OK && tc_conv_supported(pf, 3, 1) &&
+              tc_conv_prepare(pf, 3, 1, w2.data(), net->sm_count, ptrs_final, &plan, &net->device_allocs) == B200ROMP_OK && plan.kind == 34) {
+            plan.kmask = kmask;
+            op.tc = plan;
+            B2R_CUDA_OK(cudaMemcpy(op.d_bias, b2.data(), 64 * sizeof(float), cudaMemcpyHostToDevice));   // coutPad = 64
+            rc = B200ROMP_OK;
+          } else {
+            op.fold = 0;
+          }
+        }
+        if (rc != B200ROMP_OK)
+          rc = tc_conv_prepare(p, op.d.ksize, op.d.stride, op.w_host.data(), net->sm_count, ptrs_final, &op.tc, &net->device_allocs);
         if (rc == B200ROMP_OK) op.engine = B200ROMP_ENGINE_TCGEN05;
         else if (op.d.engine == B200ROMP_ENGINE_TCGEN05) return rc;
       } else if (op.d.engine == B200ROMP_ENGINE_TCGEN05) {

@@ -25,6 +25,10 @@ CASES = [
     ("k3_c64_multi_res", 3, 64, 64, 32, 24, 2, 1, 2, 1, 1, 1),
     ("k3_c32_res_many_tiles", 3, 32, 32, 64, 64, 40, 1, 2, 1, 1, 1),     # > 2 tiles per CTA and ring: double-buffered residual
     ("k3_c32", 3, 32, 32, 32, 16, 2, 1, 0, 1, 1, 1),
+    # 32->32 on internal bf16 tensors runs pixel-pair folded (net.cu fold_pixel_pairs): borders, no relu, odd batch
+    ("k3_c32_pairs_128", 3, 32, 32, 128, 128, 3, 1, 0, 1, 1, 1),
+    ("k3_c32_pairs_norelu_res", 3, 32, 32, 16, 32, 3, 0, 2, 1, 1, 1),
+    ("k3_c32_w48_unfolded", 3, 32, 32, 16, 48, 1, 1, 2, 1, 1, 1),        # odd tile count: stays on the unfolded kernels
     ("k3_c128_res", 3, 128, 128, 16, 16, 2, 1, 2, 1, 1, 1),
     ("k3_c256_res_many_tiles", 3, 256, 256, 16, 16, 24, 1, 2, 1, 1, 1),
     ("k3_c256_n32", 3, 256, 32, 32, 32, 1, 1, 0, 1, 1, 1),

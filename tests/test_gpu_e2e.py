@@ -57,6 +57,11 @@ def test_p1_maps_bf16_tolerance(params, oracle_maps):
     # run of the reference itself - we must be in that regime, not better than fp32 and not broken.
     assert ec < 0.08 and ep < 0.11          # 2x the values measured on B200 (0.039 / 0.054); maps have std 0.12 / 1.18
     assert np.corrcoef(c.cpu().numpy().ravel(), oc.numpy().ravel())[0, 1] > 0.995
+    # the 64 BasicBlock convs of the 32-channel branch run pixel-pair folded (net.cu fold_pixel_pairs) - this parity covers them
+    nb, _ = m._net(1)
+    import os
+    if os.environ.get("B200ROMP_TC_NO_FOLD") != "1":
+        assert nb.describe().count("pixel-pairs") == 64
 
 
 @pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
