@@ -116,6 +116,10 @@ int b200romp_net_num_launches(b200romp_net* net);
 /* Per-op device time of one net_run (measurement aid, bench.py / tools/op_profile.py): runs the ops one by one without
  * the CUDA graph, `iters` passes, each op bracketed by CUDA events on `stream`; us_per_op[num_launches] receives the mean. */
 int b200romp_net_profile(b200romp_net* net, int batch, int iters, float* us_per_op, b200romp_stream stream);
+/* Diagnostics: nets finalized under B200ROMP_TC_STAMPS=1 make the CTA-pair conv kernels record %globaltimer stamps
+ * (ns) of their phases; out[op][cta 0..3][16]: 0 entry, 1 prologue done, 2 predecessor grid complete, 3 weights resident,
+ * 4 first activation tile landed, 5 last MMA issued, 6 epilogue done, 7 exit.  Synchronises the device. */
+int b200romp_net_read_stamps(b200romp_net* net, unsigned long long* out, int n_ops);
 /* workspace bytes currently held */
 long long b200romp_net_workspace_bytes(b200romp_net* net);
 

@@ -136,6 +136,7 @@ def load():
     _sig(lib.b200romp_net_num_launches, i32, vp)
     _sig(lib.b200romp_net_workspace_bytes, i64, vp)
     _sig(lib.b200romp_net_profile, i32, vp, i32, i32, fp, vp)
+    _sig(lib.b200romp_net_read_stamps, i32, vp, vp, i32)
     _sig(lib.b200romp_conv2d, i32, C.POINTER(ConvDesc), fp, fp, vp, i32, i32, i32, i32, vp, i32, i32, i32, vp, i32, i32, vp)
     _sig(lib.b200romp_parse, i32, vp, vp, i32, i32, i32, f32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp)
     _sig(lib.b200romp_parse_workspace_bytes, i64, i32)
@@ -177,7 +178,7 @@ EXPORTS = [
     "b200romp_net_destroy", "b200romp_net_add_tensor", "b200romp_net_add_const_tensor", "b200romp_net_add_conv",
     "b200romp_net_add_sum", "b200romp_net_set_lane", "b200romp_net_add_maxpool",
     "b200romp_net_finalize", "b200romp_net_bind", "b200romp_net_run", "b200romp_net_read_tensor",
-    "b200romp_net_describe", "b200romp_net_num_launches", "b200romp_net_workspace_bytes", "b200romp_net_profile",
+    "b200romp_net_describe", "b200romp_net_num_launches", "b200romp_net_workspace_bytes", "b200romp_net_profile", "b200romp_net_read_stamps",
     "b200romp_conv2d",
     "b200romp_parse", "b200romp_parse_workspace_bytes", "b200romp_smpl_create", "b200romp_smpl_destroy",
     "b200romp_smpl_workspace_floats", "b200romp_smpl_forward", "b200romp_project",

@@ -50,6 +50,7 @@ struct ConvParams {
   int relu, pow_channel, out_nchw;
   int in_dtype, out_dtype, res_dtype;
   int input_norm;
+  unsigned long long* stamps;   // B200ROMP_TC_STAMPS=1: per-op timeline slots [4 CTAs][16] (%globaltimer), else null
   int debug;   // B200ROMP_TC_DEBUG bit mask (profiling experiments only): 1 = epilogue without global traffic, 2 = no MMAs, 4 = no TMA loads
 };
 

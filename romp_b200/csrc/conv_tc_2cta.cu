@@ -66,6 +66,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const uint32_t rank = cluster_ctarank();          // 0 = leader
   if (threadIdx.x == 0) {
+    tc_stamp(p, 0);                                 // kernel entry
     for (int i = 0; i < stages; ++i) {
       // EB = 2: the two TMA loads of a pair complete_tx on the leader's full[]; EB = 4: the rounding warps of both
       // CTAs arrive on it once their CTA's tile is converted
@@ -92,6 +93,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   const int per_frame = tiles_x * tiles_y;
   const int nrings = tc_num_rings(stages);
   pdl_trigger();
+  if (threadIdx.x == 0) tc_stamp(p, 1);             // prologue (barriers, TMEM, cluster sync) done
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -101,6 +103,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       for (int i = 0; i < Cfg::TAPS * Cfg::KCH; ++i)
         bulk_copy_g2s(sB + (size_t)i * Cfg::BTILE, wsrc + (size_t)i * Cfg::BTILE, Cfg::BTILE, b_full);
       pdl_wait();
+      tc_stamp(p, 2);                               // predecessor grid complete
       const uint64_t pol = l2_policy_stream(p.debug);
       int stage = 0, stage_other = 0;
       uint32_t phase = 0, phase_other = 0;
@@ -115,6 +118,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
           if (EB == 4) {
             mbar_arrive_expect_tx(&landed[sidx], Cfg::STAGE_PAYLOAD);
             tma_load_4d(sA + (size_t)sidx * Cfg::STAGE_BYTES, &tmap, &landed[sidx], c * Cfg::CW, x0 - 1, y0 - 1, n, pol);
+          } else if (p.debug & 4) {                 // profiling experiment: no activation loads
+            if (rank == 0) mbar_arrive(&full[sidx]);
           } else {
             if (rank == 0) mbar_arrive_expect_tx(&full[sidx], 2 * Cfg::STAGE_PAYLOAD);      // own tile + the peer's
             tma_load_4d_2cta(sA + (size_t)sidx * Cfg::STAGE_BYTES, &tmap, &full[sidx], c * Cfg::CW, x0 - 1, y0 - 1, n, pol);
@@ -136,6 +141,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       mbar_wait(b_full, 0);
       mbar_wait(b_peer, 0);
       tc_fence_after();
+      if (warp == 1) tc_stamp(p, 3);                // weight slabs of both CTAs resident
       const uint32_t b_base = smem_u32(sB);
       const int rbase = tc_ring_base(stages, warp - 1), rsize = tc_ring_size(stages, warp - 1);
       int stage = 0;
@@ -151,6 +157,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
           const int sidx = rbase + stage;
           mbar_wait(&full[sidx], phase);
           tc_fence_after();
+          if (warp == 1 && it == 0 && c == 0) tc_stamp(p, 4);   // first activation tile landed
           const uint32_t a_base = smem_u32(sA + (size_t)sidx * Cfg::STAGE_BYTES);
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
@@ -162,6 +169,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
               // channel half of this K step: which of the two chunks (KCH = 2) or which half of the row (KCH = 1)
               const int half = Cfg::KCH == 2 ? c : (Cfg::KCH == 1 ? k / (Cfg::KSTEPS / 2) : 0);
               if (Cfg::KCH <= 2 && !((kmask >> (t * 2 + half)) & 1u)) continue;   // folded conv: this weight block is all zero
+              if (p.debug & 2) continue;                                          // profiling experiment: no MMAs
               const uint64_t adesc = make_smem_desc(a_tap + k * 32, Cfg::HW_ * Cfg::ROWB, Cfg::LAYOUT);
               const uint64_t bdesc = make_smem_desc(b_tap + k * 32, 8 * Cfg::ROWB, Cfg::LAYOUT);
               umma_any<EB, true>(d_tile, adesc, bdesc, Cfg::IDESC, mma_i > 0 ? 1u : 0u);
@@ -173,6 +181,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         }
         umma_commit_2cta(&tmem_full[acc]);         // both halves of the accumulator complete -> both epilogues
       }
+      if (warp == 1) tc_stamp(p, 5);                // last MMA of this ring issued
     }
   } else if (EB == 4 && warp >= kFirstCvtWarp) {
     // ===================== TF32 rounding warps (both CTAs): landed -> round in place -> full (on the leader) =====================
@@ -205,11 +214,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       tc_epilogue_loop_tma<NT, true>(p, epi_maps, tma_epi, epi_smem, res_bar, tmem_base, tmem_full, tmem_empty, s_bias, tiles_x,
                                      per_frame, num_tiles);
   }
+  if (threadIdx.x == kFirstEpiWarp * 32) tc_stamp(p, 6);   // first epilogue warp finished its last tile
   tc_fence_before();
   cluster_sync_all();                               // no CTA leaves while its peer may still address its barriers / TMEM
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
+    if ((threadIdx.x & 31) == 0) tc_stamp(p, 7);    // kernel exit
   }
 }
 

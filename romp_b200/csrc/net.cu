@@ -79,6 +79,7 @@ struct b200romp_net {
   std::vector<cudaEvent_t> op_done;     // one event per op, recorded on the op's lane during capture
   cudaEvent_t fork_ev = nullptr;
   bool use_lanes = false;
+  unsigned long long* d_stamps = nullptr;   // B200ROMP_TC_STAMPS=1: [ops][4 CTAs][16] %globaltimer stamps (b200romp_net_read_stamps)
 };
 
 static int fill_params(b200romp_net* net, const Op& op, int batch, ConvParams* out) {
@@ -102,6 +103,7 @@ static int fill_params(b200romp_net* net, const Op& op, int batch, ConvParams* o
   p.relu = d.relu; p.pow_channel = d.pow_channel; p.out_nchw = to.nchw;
   p.in_dtype = ti.dtype; p.out_dtype = to.dtype; p.input_norm = d.input_norm;
   { static const int dbg = getenv("B200ROMP_TC_DEBUG") ? atoi(getenv("B200ROMP_TC_DEBUG")) : 0; p.debug = dbg; }
+  if (net->d_stamps) p.stamps = net->d_stamps + (size_t)(&op - net->ops.data()) * 64;
   if (op.fold) {   // the same bytes seen as [B, H, W/2, 2C]: two horizontally adjacent pixels form one 64-channel pixel
     p.Win /= 2; p.Wout /= 2;
     p.in_C *= 2; p.cin *= 2; p.out_C *= 2; p.cout *= 2; p.res_C *= 2;
@@ -439,6 +441,12 @@ int b200romp_net_finalize(b200romp_net* net, int max_batch) {
   for (int t = 0; t < nT; ++t)
     if (tensor_buf[t] >= 0) net->tensors[t].ptr = net->workspace + bufs[tensor_buf[t]].offset;
   net->max_batch = max_batch;
+  { const char* e = getenv("B200ROMP_TC_STAMPS");
+    if (e && e[0] == '1') {
+      B2R_CUDA_OK(cudaMalloc(&net->d_stamps, (size_t)nO * 64 * sizeof(unsigned long long)));
+      net->device_allocs.push_back(net->d_stamps);
+      B2R_CUDA_OK(cudaMemset(net->d_stamps, 0, (size_t)nO * 64 * sizeof(unsigned long long)));
+    } }
   // ---- engine resolution + weight upload
   for (int i = 0; i < nO; ++i) {
     Op& op = net->ops[i];
@@ -636,6 +644,15 @@ int b200romp_net_run(b200romp_net* net, int batch, b200romp_stream stream_) {
     it = net->graphs.insert({key, exec}).first;
   }
   B2R_CUDA_OK(cudaGraphLaunch(it->second, stream));
+  return B200ROMP_OK;
+}
+
+int b200romp_net_read_stamps(b200romp_net* net, unsigned long long* out, int n_ops) {
+  B2R_REQUIRE(net && out && n_ops > 0 && n_ops <= (int)net->ops.size(), "read_stamps: bad arguments");
+  B2R_REQUIRE(net->d_stamps, "read_stamps: the net was not finalized under B200ROMP_TC_STAMPS=1");
+  B2R_CUDA_OK(cudaSetDevice(net->device));
+  B2R_CUDA_OK(cudaDeviceSynchronize());
+  B2R_CUDA_OK(cudaMemcpy(out, net->d_stamps, (size_t)n_ops * 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return B200ROMP_OK;
 }
 

@@ -53,6 +53,14 @@ __device__ __forceinline__ bool elect_one() {
 // Programmatic dependent launch: the next conv of the stream may start its prologue (barrier init, TMEM allocation,
 // weight-slab copy - all independent of activations) while this grid drains; pdl_wait() then blocks until every
 // predecessor grid has completed and its writes are visible.  Both are no-ops for a launch without the attribute.
+// timeline probe (diagnostics): one %globaltimer stamp per (CTA < 4, slot); p.stamps is null in normal runs
+__device__ __forceinline__ void tc_stamp(const ConvParams& p, int slot) {
+  if (p.stamps != nullptr && blockIdx.x < 4 && blockIdx.y == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.stamps[blockIdx.x * 16 + slot] = t;
+  }
+}
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
