@@ -10,6 +10,7 @@ channels); every per-frame FLOP runs in the CUDA library.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -198,8 +199,22 @@ def build_backbone(nb: NetBuilder, sd, in_dtype):
     frames = nb.tensor(512, 512, 3, in_dtype, external=1, name="frames")
     p = "backbone."
     x = cb(frames, p + "conv1", p + "bn1", stride=2, relu=True, input_norm=1)   # model.py:385-387
-    x = cb(x, p + "conv2", p + "bn2", stride=2, relu=True)                                                # :388-390
-    for i in range(4):                                                                                     # layer1, :391
+    # layer1.0 (Bottleneck with a 1x1 downsample on the skip, model.py:93-120,391): relu(bn3(conv3(t)) + bnd(convd(x))) is ONE
+    # 1x1 conv over the channel concatenation [t | x] with weights [W3 | Wd] and bias b3 + bd.  conv2 of the stem and
+    # conv2 of the block write the two halves of that 128-channel tensor, so the 256-channel downsample output (0.5 GB
+    # per 64 frames, written once and read once as a residual) never exists.
+    q = p + "layer1.0."
+    fuse_skip = (q + "downsample.0.weight") in sd and os.environ.get("B200ROMP_NO_SKIP_CONCAT") != "1"
+    if fuse_skip:
+        cat = nb.tensor(nb.shape[x][0] // 2, nb.shape[x][1] // 2, 128)
+        cb(x, p + "conv2", p + "bn2", stride=2, relu=True, out=cat, out_c_off=64)                          # :388-390
+        y = cb(cat, q + "conv1", q + "bn1", relu=True, in_c_off=64)
+        cb(y, q + "conv2", q + "bn2", relu=True, out=cat, out_c_off=0)
+        (w3, b3), (wd, bd) = fold_bn(sd, q + "conv3", q + "bn3"), fold_bn(sd, q + "downsample.0", q + "downsample.1")
+        x = nb.conv(cat, np.concatenate([w3, wd], axis=1), b3 + bd, relu=True)
+    else:
+        x = cb(x, p + "conv2", p + "bn2", stride=2, relu=True)
+    for i in range(1 if fuse_skip else 0, 4):                                                              # layer1, :391
         q = f"{p}layer1.{i}."
         y = cb(x, q + "conv1", q + "bn1", relu=True)
         y = cb(y, q + "conv2", q + "bn2", relu=True)
