@@ -299,8 +299,26 @@ __device__ __forceinline__ void sum_load8(const void* p, uint32_t chunk, float (
     for (int k = 0; k < 4; ++k) { v[2 * k] = __uint_as_float(w[k] << 16); v[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u); }
   }
 }
+// raw 8-element chunk: loads are issued first (registers: 4 for bf16, 8 for fp32), converted / accumulated later
+template <int DT> struct SumRaw { uint4 a, b; };
 template <int DT>
-__global__ void __launch_bounds__(256) fuse_sum_pipe_kernel(const SumParams p, int c8n, int c8_shift, int4 up_shift, int row_bytes) {
+__device__ __forceinline__ void sum_load_raw(const void* p, uint32_t chunk, SumRaw<DT>& r) {
+  if (DT == B200ROMP_F32) { r.a = reinterpret_cast<const uint4*>(p)[2 * chunk]; r.b = reinterpret_cast<const uint4*>(p)[2 * chunk + 1]; }
+  else r.a = reinterpret_cast<const uint4*>(p)[chunk];
+}
+template <int DT>
+__device__ __forceinline__ void sum_raw_to_float(const SumRaw<DT>& r, float (&v)[8]) {
+  if (DT == B200ROMP_F32) {
+    v[0] = __uint_as_float(r.a.x); v[1] = __uint_as_float(r.a.y); v[2] = __uint_as_float(r.a.z); v[3] = __uint_as_float(r.a.w);
+    v[4] = __uint_as_float(r.b.x); v[5] = __uint_as_float(r.b.y); v[6] = __uint_as_float(r.b.z); v[7] = __uint_as_float(r.b.w);
+  } else {
+    const uint32_t w[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[2 * k] = __uint_as_float(w[k] << 16); v[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u); }
+  }
+}
+template <int DT>
+__global__ void __launch_bounds__(256, DT == B200ROMP_F32 ? 3 : 4) fuse_sum_pipe_kernel(const SumParams p, int c8n, int c8_shift, int4 up_shift, int row_bytes) {
   extern __shared__ uint8_t sum_smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sum_smem_raw) + 127) & ~(uintptr_t)127);
   uint64_t* full = reinterpret_cast<uint64_t*>(sm + (size_t)kSumStages * row_bytes);
@@ -341,32 +359,52 @@ __global__ void __launch_bounds__(256) fuse_sum_pipe_kernel(const SumParams p, i
                               : nullptr;
     uint8_t* orow = reinterpret_cast<uint8_t*>(p.out) + (size_t)row * row_bytes;
     mbar_wait(&full[st], ph);
-    for (int i = threadIdx.x; i < per_row; i += blockDim.x) {
-      const int x = c8_shift >= 0 ? (i >> c8_shift) : i / c8n, c8 = i - x * c8n;
-      float s[8], t[8];
-      sum_load8<DT>(srow, i, s);                            // generic load from shared memory
+    // two chunks per thread and trip: all loads of both chunks are issued before the first store (the output may alias
+    // nothing, but the compiler cannot know) - twice the bytes in flight per warp (ncu: long-scoreboard bound)
+    constexpr int U = DT == B200ROMP_F32 ? 1 : 2;           // fp32 chunks are twice the registers: one per trip
+    for (int i0 = threadIdx.x; i0 < per_row; i0 += U * blockDim.x) {
+      const int i1 = i0 + blockDim.x;
+      const bool two = U == 2 && i1 < per_row;
+      SumRaw<DT> rb[U], rt[U][4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (k < p.n_terms) {
-          sum_load8<DT>(trow[k], (uint32_t)((x >> ush[k]) * c8n + c8), t);
+      for (int u = 0; u < U; ++u) {
+        const int i = u ? i1 : i0;
+        if (u && !two) break;
+        const int x = c8_shift >= 0 ? (i >> c8_shift) : i / c8n, c8 = i - x * c8n;
+        sum_load_raw<DT>(srow, i, rb[u]);                   // generic load from shared memory
 #pragma unroll
-          for (int j = 0; j < 8; ++j) s[j] += t[j];         // order: base, term 0, 1, ...
+        for (int k = 0; k < 4; ++k)
+          if (k < p.n_terms) sum_load_raw<DT>(trow[k], (uint32_t)((x >> ush[k]) * c8n + c8), rt[u][k]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = u ? i1 : i0;
+        if (u && !two) break;
+        float s[1][8], t[8];
+        sum_raw_to_float<DT>(rb[u], s[0]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (k < p.n_terms) {
+            sum_raw_to_float<DT>(rt[u][k], t);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[0][j] += t[j];     // order: base, term 0, 1, ...
+          }
         }
-      }
-      if (p.relu) {
+        if (p.relu) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s[j] = fmaxf(s[j], 0.f);
-      }
-      if (DT == B200ROMP_F32) {
-        reinterpret_cast<float4*>(orow)[2 * i] = make_float4(s[0], s[1], s[2], s[3]);
-        reinterpret_cast<float4*>(orow)[2 * i + 1] = make_float4(s[4], s[5], s[6], s[7]);
-      } else {
-        uint4 pk;
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(s[0], s[1]), h1 = __floats2bfloat162_rn(s[2], s[3]);
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(s[4], s[5]), h3 = __floats2bfloat162_rn(s[6], s[7]);
-        pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-        pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-        reinterpret_cast<uint4*>(orow)[i] = pk;
+          for (int j = 0; j < 8; ++j) s[0][j] = fmaxf(s[0][j], 0.f);
+        }
+        if (DT == B200ROMP_F32) {
+          reinterpret_cast<float4*>(orow)[2 * i] = make_float4(s[0][0], s[0][1], s[0][2], s[0][3]);
+          reinterpret_cast<float4*>(orow)[2 * i + 1] = make_float4(s[0][4], s[0][5], s[0][6], s[0][7]);
+        } else {
+          uint4 pk;
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(s[0][0], s[0][1]), h1 = __floats2bfloat162_rn(s[0][2], s[0][3]);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(s[0][4], s[0][5]), h3 = __floats2bfloat162_rn(s[0][6], s[0][7]);
+          pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+          pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+          reinterpret_cast<uint4*>(orow)[i] = pk;
+        }
       }
     }
     __syncwarp();

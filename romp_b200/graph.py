@@ -117,19 +117,24 @@ class NetBuilder:
             w = round_bf16(w)      # both engines then see identical bf16-representable weights
         bp = None if b is None else np.ascontiguousarray(b, dtype=np.float32)
         self.flops_per_frame += 2 * cout * cin * kh * kw * (Ho // up) * (Wo // up)
-        if self.precision == "tf32" and k == 3 and stride == 2 and cin == 256 and res is None and up == 1:
-            # fp32 weights of a 256-channel 3x3 slab do not fit next to the pipeline in shared memory: split K into
-            # two 128-channel convs, the second accumulating onto the first (fp32 intermediate, no rounding in between)
-            H, W, _, _ = self.shape[x]
-            part = self.tensor(Ho, Wo, cout, F32)
-            d0 = ConvDesc(x, in_c_off, part, 0, -1, 0, 0, 128, cout, k, stride, 0, 1, input_norm, -1, d.engine)
-            d1 = ConvDesc(x, in_c_off + 128, out, out_c_off, part, 0, 0, 128, cout, k, stride, int(relu), 1, input_norm,
-                          pow_channel, d.engine)
-            for dd, ws, bb in ((d0, w[:, :128], bp), (d1, w[:, 128:], None)):
-                ws = np.ascontiguousarray(ws)
+        ksplit = self.precision == "tf32" or (self.precision == "bf16" and os.environ.get("B200ROMP_NO_S2_KSPLIT") != "1")
+        if ksplit and k == 3 and stride == 2 and cin == 256 and res is None and up == 1:
+            # the weights of a 256-channel 3x3 slab (fp32: 295 KB; bf16: 147 KB at N = 32) leave no room for a pipeline in
+            # shared memory: split K into 128-channel convs, each accumulating onto the previous one (fp32
+            # intermediates, no rounding in between)
+            pc = 128 if self.precision == "tf32" else int(os.environ.get("B200ROMP_S2_KSPLIT_C", "128"))   # channels per part
+            n_parts, prev = cin // pc, -1
+            for i in range(n_parts):
+                last = i == n_parts - 1
+                dst = out if last else self.tensor(Ho, Wo, cout, F32)
+                dd = ConvDesc(x, in_c_off + i * pc, dst, out_c_off if last else 0, prev, 0, 0, pc, cout, k, stride,
+                              int(relu) if last else 0, 1, input_norm, pow_channel if last else -1, d.engine)
+                ws = np.ascontiguousarray(w[:, i * pc:(i + 1) * pc])
+                bb = bp if i == 0 else None
                 self._added(_lib.check(self.lib.b200romp_net_add_conv(
                     self.net, C.byref(dd), ws.ctypes.data_as(C.POINTER(C.c_float)),
                     None if bb is None else bb.ctypes.data_as(C.POINTER(C.c_float))), "add_conv"))
+                prev = dst
             return out
         self._added(_lib.check(self.lib.b200romp_net_add_conv(
             self.net, C.byref(d), w.ctypes.data_as(C.POINTER(C.c_float)),

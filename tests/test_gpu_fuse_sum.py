@@ -13,7 +13,8 @@ TD = {F32: torch.float32, BF16: torch.bfloat16}
 
 
 @pytest.mark.parametrize("dtype", [F32, BF16])
-@pytest.mark.parametrize("H,W,Cc,ups", [(32, 32, 32, [2, 4, 8]), (16, 16, 64, [1, 2]), (8, 8, 256, [1])])
+@pytest.mark.parametrize("H,W,Cc,ups", [(32, 32, 32, [2, 4, 8]), (16, 16, 64, [1, 2]), (8, 8, 256, [1]),
+                                        (128, 128, 32, [2, 4, 8]), (32, 96, 32, [2])])   # last two: two chunks per thread / ragged second chunk
 def test_fuse_sum_matches_torch(dtype, H, W, Cc, ups):
     lib = _lib.load()
     dev = torch.device("cuda", 0)
