@@ -86,13 +86,16 @@ int b200romp_net_add_conv(b200romp_net* net, const b200romp_conv_desc* desc, con
 /* Fuse-layer summation of HighResolutionModule.forward (simple_romp/romp/model.py:226-244, nearest upsampling of the
  * higher-index branches :188-197) as ONE elementwise op instead of a chain of residual adds:
  *   out[n,y,x,c] = act( base[n,y,x,c] + sum_k term_k[n, y/up_k, x/up_k, c] ),  summed in fp32 in the order base, term 0, 1, ..
- * All tensors NHWC with the same C (multiple of 8); term k is [H/up_k, W/up_k, C]; dtypes per tensor (bf16/fp32). */
+ * All tensors NHWC, C a multiple of 8; term k is [H/up_k, W/up_k, C_k] with C_k >= C and contributes its channel slice
+ * [term_c_off_k, term_c_off_k + C) - several fuse terms computed from one branch by ONE merged 1x1 conv live in one tensor;
+ * dtypes per tensor (bf16/fp32). */
 typedef struct b200romp_sum_desc {
   int out, base;           /* output / identity-term tensor ids, both [H,W,C]                           */
   int n_terms;             /* 1..4                                                                      */
   int term[4];             /* tensor ids                                                                */
   int up[4];               /* 1, 2, 4, 8: nearest-neighbour replication factor of term k                */
   int relu;                /* 1 = ReLU after the sum (model.py:243)                                     */
+  int term_c_off[4];       /* first channel of term k inside its tensor (multiple of 8; 0 = whole tensor) */
 } b200romp_sum_desc;
 /* Returns op id (ops run in the order they were added, convs and sums alike). */
 int b200romp_net_add_sum(b200romp_net* net, const b200romp_sum_desc* desc);

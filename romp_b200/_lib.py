@@ -28,7 +28,7 @@ class ConvDesc(C.Structure):
 
 class SumDesc(C.Structure):
     _fields_ = [("out", C.c_int), ("base", C.c_int), ("n_terms", C.c_int), ("term", C.c_int * 4), ("up", C.c_int * 4),
-                ("relu", C.c_int)]
+                ("relu", C.c_int), ("term_c_off", C.c_int * 4)]
 
 
 class BevWeights(C.Structure):

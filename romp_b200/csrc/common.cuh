@@ -136,6 +136,7 @@ struct SumParams {
   void* out;
   int base_dt, term_dt[4], out_dt;
   int n_terms, up[4];
+  int term_C[4], term_c_off[4];   // channels of the term tensors (>= C) and the first channel of the slice that is added
   int B, H, W, C, relu;
 };
 int launch_fuse_sum(const SumParams& p, cudaStream_t stream);

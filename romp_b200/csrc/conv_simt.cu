@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(256) fuse_sum_kernel(const SumParams p, int c8
         if (k < p.n_terms) {
           const int sh = ush[k];
           const size_t tp = ((size_t)n * (p.H >> sh) + (y >> sh)) * (p.W >> sh) + (x >> sh);
-          load8(p.term[k], p.term_dt[k], tp * p.C + c8 * 8, t);
+          load8(p.term[k], p.term_dt[k], tp * p.term_C[k] + p.term_c_off[k] + c8 * 8, t);
 #pragma unroll
           for (int j = 0; j < 8; ++j) s[j] += t[j];
         }
@@ -324,6 +324,7 @@ __global__ void __launch_bounds__(256, DT == B200ROMP_F32 ? 3 : 4) fuse_sum_pipe
   uint64_t* full = reinterpret_cast<uint64_t*>(sm + (size_t)kSumStages * row_bytes);
   uint64_t* empty = full + kSumStages;
   const int ush[4] = {up_shift.x, up_shift.y, up_shift.z, up_shift.w};
+  const int tc8n[4] = {p.term_C[0] >> 3, p.term_C[1] >> 3, p.term_C[2] >> 3, p.term_C[3] >> 3};   // 16 B chunks per term pixel
   const int rows = p.B * p.H, per_row = p.W * c8n;
   const int lane = threadIdx.x & 31;
   const uint8_t* base = reinterpret_cast<const uint8_t*>(p.base);
@@ -351,11 +352,11 @@ __global__ void __launch_bounds__(256, DT == B200ROMP_F32 ? 3 : 4) fuse_sum_pipe
     const uint32_t ph = (uint32_t)(iter / kSumStages) & 1u;
     const int n = row / p.H, y = row - n * p.H;
     const uint8_t* srow = sm + (size_t)st * row_bytes;
-    const uint8_t* trow[4];                                  // term rows feeding this output row
+    const uint8_t* trow[4];                                  // term rows feeding this output row (start of the channel slice)
 #pragma unroll
     for (int k = 0; k < 4; ++k)
       trow[k] = k < p.n_terms ? reinterpret_cast<const uint8_t*>(p.term[k]) +
-                                    ((size_t)n * (p.H >> ush[k]) + (y >> ush[k])) * (size_t)(p.W >> ush[k]) * p.C * ES
+                                    (((size_t)n * (p.H >> ush[k]) + (y >> ush[k])) * (size_t)(p.W >> ush[k]) * p.term_C[k] + p.term_c_off[k]) * ES
                               : nullptr;
     uint8_t* orow = reinterpret_cast<uint8_t*>(p.out) + (size_t)row * row_bytes;
     mbar_wait(&full[st], ph);
@@ -374,7 +375,7 @@ __global__ void __launch_bounds__(256, DT == B200ROMP_F32 ? 3 : 4) fuse_sum_pipe
         sum_load_raw<DT>(srow, i, rb[u]);                   // generic load from shared memory
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          if (k < p.n_terms) sum_load_raw<DT>(trow[k], (uint32_t)((x >> ush[k]) * c8n + c8), rt[u][k]);
+          if (k < p.n_terms) sum_load_raw<DT>(trow[k], (uint32_t)((x >> ush[k]) * tc8n[k] + c8), rt[u][k]);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {

@@ -240,8 +240,10 @@ int b200romp_net_add_sum(b200romp_net* net, const b200romp_sum_desc* desc) {
     const Tensor& tt = T[desc->term[k]];
     const int u = desc->up[k];
     B2R_REQUIRE(u == 1 || u == 2 || u == 4 || u == 8, "add_sum: up must be 1,2,4,8");
-    B2R_REQUIRE(!tt.nchw && tt.dtype != B200ROMP_U8 && tt.C == to.C && tt.H * u == to.H && tt.W * u == to.W,
-                "add_sum: term %d is %dx%dx%d, expected %dx%dx%d", k, tt.H, tt.W, tt.C, to.H / u, to.W / u, to.C);
+    const int co = desc->term_c_off[k];
+    B2R_REQUIRE(!tt.nchw && tt.dtype != B200ROMP_U8 && tt.C % 8 == 0 && co >= 0 && co % 8 == 0 && co + to.C <= tt.C &&
+                    tt.H * u == to.H && tt.W * u == to.W,
+                "add_sum: term %d is %dx%dx%d (slice from channel %d), expected %dx%dx%d", k, tt.H, tt.W, tt.C, co, to.H / u, to.W / u, to.C);
   }
   Op op;
   op.kind = 1;
@@ -281,6 +283,7 @@ static int fill_sum_params(b200romp_net* net, const Op& op, int batch, SumParams
     const Tensor& tt = net->tensors[op.sum.term[k]];
     B2R_REQUIRE(tt.ptr, "sum op: unbound term tensor");
     p.term[k] = tt.ptr; p.term_dt[k] = tt.dtype; p.up[k] = op.sum.up[k];
+    p.term_C[k] = tt.C; p.term_c_off[k] = op.sum.term_c_off[k];
   }
   p.B = batch; p.H = to.H; p.W = to.W; p.C = to.C; p.relu = op.sum.relu;
   *out = p;

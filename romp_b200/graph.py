@@ -141,12 +141,15 @@ class NetBuilder:
             None if bp is None else bp.ctypes.data_as(C.POINTER(C.c_float))), "add_conv"))
         return out
 
-    def sum(self, base, terms, ups, relu=True, out_dtype=None, name=None):
-        """out = act(base + sum_k nearest_up(terms[k], ups[k])) - the HRNet fuse-layer summation (model.py:226-244)."""
+    def sum(self, base, terms, ups, relu=True, out_dtype=None, name=None, c_offs=None):
+        """out = act(base + sum_k nearest_up(terms[k][..., c_offs[k]:c_offs[k]+C], ups[k])) - the HRNet fuse-layer summation
+        (model.py:226-244); a term may be a channel slice of a wider tensor (merged 1x1 convs)."""
         H, W, Cc, _ = self.shape[base]
         out = self.tensor(H, W, Cc, out_dtype, name=name)
+        c_offs = [0] * len(terms) if c_offs is None else list(c_offs)
         d = SumDesc(out, base, len(terms), (C.c_int * 4)(*(list(terms) + [0] * (4 - len(terms)))),
-                    (C.c_int * 4)(*(list(ups) + [1] * (4 - len(ups)))), int(relu))
+                    (C.c_int * 4)(*(list(ups) + [1] * (4 - len(ups)))), int(relu),
+                    (C.c_int * 4)(*(c_offs + [0] * (4 - len(c_offs)))))
         self._added(_lib.check(self.lib.b200romp_net_add_sum(self.net, C.byref(d)), "add_sum"))
         return out
 
@@ -246,15 +249,40 @@ def build_backbone(nb: NetBuilder, sd, in_dtype):
                 for k in range(4):
                     xs[b] = basic_block(xs[b], f"{q}branches.{b}.{k}.")
         outs = []
-        for i in range(nbr if multi else 1):
-            terms, ups = [], []
+        n_out = nbr if multi else 1
+        # The 1x1 fuse convs that read the same branch j (one per output i < j, model.py:188-197) are ONE conv with the
+        # output channels concatenated (zero-padded to a multiple of 64): the sums read channel slices of its output.
+        merged = {}
+        if os.environ.get("B200ROMP_NO_FUSE1X1_MERGE") != "1":
+            for j in range(1, nbr):
+                tgt = [i for i in range(n_out) if i < j]
+                if len(tgt) < 2:
+                    continue
+                folded = [fold_bn(sd, f"{q}fuse_layers.{i}.{j}.0", f"{q}fuse_layers.{i}.{j}.1") for i in tgt]
+                ctot = sum(w.shape[0] for w, _ in folded)
+                pad = (-ctot) % 64
+                wcat = np.concatenate([w for w, _ in folded] + ([np.zeros((pad,) + folded[0][0].shape[1:], np.float32)] if pad else []), 0)
+                bcat = np.concatenate([b for _, b in folded] + ([np.zeros(pad, np.float32)] if pad else []), 0)
+                with nb.on_lane(j):
+                    t = nb.conv(xs[j], wcat, bcat)
+                off = 0
+                for i, (w, _) in zip(tgt, folded):
+                    merged[(i, j)] = (t, off)
+                    off += w.shape[0]
+        for i in range(n_out):
+            terms, ups, offs = [], [], []
             for j in range(nbr):
                 if j == i:
                     continue                  # identity term (model.py:236-239) is the base of the sum
                 r = f"{q}fuse_layers.{i}.{j}."
                 with nb.on_lane(j):           # a fuse term is computed from branch j alone
-                    if j > i:                 # 1x1 conv + BN, nearest upsample folded into the sum (model.py:188-197)
+                    if (i, j) in merged:
+                        terms.append(merged[(i, j)][0])
+                        offs.append(merged[(i, j)][1])
+                        ups.append(2 ** (j - i))
+                    elif j > i:               # 1x1 conv + BN, nearest upsample folded into the sum (model.py:188-197)
                         terms.append(cb(xs[j], r + "0", r + "1"))
+                        offs.append(0)
                         ups.append(2 ** (j - i))
                     else:                     # chain of stride-2 3x3 convs (model.py:200-218)
                         t = xs[j]
@@ -262,9 +290,10 @@ def build_backbone(nb: NetBuilder, sd, in_dtype):
                             t = cb(t, f"{r}{k}.0", f"{r}{k}.1", stride=2, relu=True)
                         k = i - j - 1
                         terms.append(cb(t, f"{r}{k}.0", f"{r}{k}.1", stride=2))
+                        offs.append(0)
                         ups.append(1)
             with nb.on_lane(i):
-                acc = nb.sum(xs[i], terms, ups, relu=True)
+                acc = nb.sum(xs[i], terms, ups, relu=True, c_offs=offs)
             outs.append(acc)
         return outs
 
