@@ -164,7 +164,8 @@ b200romp_smpl* b200romp_smpl_create(int device, int n_betas, const float* v_temp
                                     const long long* parents /*[24]*/, const long long* extra_joints_index /*[21]*/,
                                     const float* J_regressor_extra9 /*[9,6890]*/, const float* J_regressor_h36m17 /*[17,6890]*/);
 void b200romp_smpl_destroy(b200romp_smpl* smpl);
-/* floats of caller-provided device workspace needed per person */
+/* floats of caller-provided device workspace needed per person: smpl_forward(n, ...) uses n x this many floats; the
+ * contents are opaque scratch (per-person operands followed by the coordinate-tile-major v_posed of the blend GEMM) */
 int b200romp_smpl_workspace_floats(void);
 /* betas [n,betas_stride>=n_betas] (first n_betas used), thetas [n,72] -> verts [n,6890,3], joints [n,71,3].
  * If d_count != NULL the number of persons is min(n, *d_count) read on the device (no host sync). */

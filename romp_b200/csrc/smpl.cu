@@ -26,13 +26,15 @@ namespace b200romp {
 
 constexpr int kV = 6890;
 constexpr int kJ = 24;
-// per-person scratch record (floats): [0,224) features | [224,512) A[24][12] | [512,848) 448 fp16 (hi | lo split of the features,
-// the tensor-core blend's left operand) | [848,1424) skinning operand | [1424, 1424+20736) v_posed written by the blend GEMM, read
-// by the skinning kernel
+// workspace = `cap` per-person records of kWsHead floats, then v_posed.  Record: [0,224) features | [224,512) A[24][12] |
+// [512,848) 448 fp16 (hi | lo split of the features, the tensor-core blend's left operand) | [848,1424) skinning operand.
+// v_posed (written by the blend GEMM, read by the skinning kernel) is stored COORDINATE-TILE major, [81][cap][256] floats: a
+// 256-person x 256-coordinate tile of the GEMM is one contiguous 256 KB block.  (Person-major rows of 20,736 floats made
+// every 4 KB TMA store 32 scattered 128 B segments 88 KB apart: 2.8 TB/s of HBM writes.)
 constexpr int kBlendCols = 20736;
 constexpr int kSkinOff = 848;            // [848, 1424): skinning operand A' = 12 rows x 96 fp16 ([A_hi | A_hi | A_lo] per transform entry)
 constexpr int kWsHead = 1424;
-constexpr int kWsFloats = kWsHead + kBlendCols;
+constexpr int kWsFloats = kWsHead + kBlendCols;      // floats per person of capacity (b200romp_smpl_workspace_floats)
 constexpr int kFeatOff = 0, kAOff = 224, kAqOff = 512;
 constexpr int kMaxBetas = 16;
 
@@ -49,7 +51,7 @@ struct SmplDev {
   const int* csr_rowptr;        // [27]
   const int* csr_col;
   const float* csr_val;
-  const __half* blend_q;        // [20736][672] fp16: B' = [B_hi | B_hi | B_lo] per vertex coordinate (smpl_blend_tc.cu)
+  const __half* blend_q;        // [20736][448] fp16: B' = [B_hi | B_lo] per vertex coordinate (smpl_blend_tc.cu)
   const __half* skin_w;         // [6912][96] fp16: W' = [W_hi | W_lo | W_hi] per vertex, 24 joints padded to 32
   const float* vt_pad;          // [20736] v_template, zero padded
 };
@@ -57,7 +59,7 @@ struct SmplDev {
 // smpl_blend_tc.cu
 int smpl_blend_tc_launch(const void* a_rows, int a_row_stride_bytes, int capacity, const void* b_rows, float* v_posed, const float* v_template_pad,
                          int n, const int* d_count, int sm_count, cudaStream_t stream);
-int smpl_skin_tc_launch(const void* w_rows, const void* ws_base, int a_off_bytes, int vp_off_floats, int row_stride_bytes, int capacity, int n,
+int smpl_skin_tc_launch(const void* w_rows, const void* ws_base, int a_off_bytes, const float* v_posed, int row_stride_bytes, int capacity, int n,
                         const int* d_count, int sm_count, float* verts, cudaStream_t stream);
 
 __device__ __forceinline__ int person_count(int n, const int* d_count) {
@@ -74,7 +76,7 @@ __global__ void __launch_bounds__(128) smpl_pose_kernel(SmplDev m, const float* 
   const int n = blockIdx.x * 4 + warp;
   const int N = person_count(n_host, d_count);
   if (n >= N) return;    // whole warp exits together; only __syncwarp is used below
-  float* w = ws + (size_t)n * kWsFloats;
+  float* w = ws + (size_t)n * kWsHead;
   const float* be = betas + (size_t)n * betas_stride;
   float R[9], Jl[3] = {0.f, 0.f, 0.f};
   if (lane < m.n_betas) w[kFeatOff + lane] = be[lane];
@@ -190,11 +192,11 @@ __global__ void __launch_bounds__(256) smpl_verts_kernel(SmplDev m, int n_host, 
   const int K = m.K;
   for (int i = tid; i < K * kPT; i += 256) {
     const int q = i % kPT, p = i / kPT;
-    s_feat[p * kPT + q] = (n0 + q < N) ? ws[(size_t)(n0 + q) * kWsFloats + kFeatOff + p] : 0.f;
+    s_feat[p * kPT + q] = (n0 + q < N) ? ws[(size_t)(n0 + q) * kWsHead + kFeatOff + p] : 0.f;
   }
   for (int i = tid; i < kPT * 288; i += 256) {
     const int q = i / 288, e = i % 288;
-    s_A[i] = (n0 + q < N) ? ws[(size_t)(n0 + q) * kWsFloats + kAOff + e] : 0.f;
+    s_A[i] = (n0 + q < N) ? ws[(size_t)(n0 + q) * kWsHead + kAOff + e] : 0.f;
   }
   __syncthreads();
   const int half = tid >> 7;
@@ -260,7 +262,7 @@ __global__ void __launch_bounds__(256) smpl_skin_kernel(SmplDev m, int n_host, c
   const int tid = threadIdx.x;
   for (int i = tid; i < kPT * 288; i += 256) {
     const int q = i / 288, e = i % 288;
-    s_A[i] = (n0 + q < N) ? ws[(size_t)(n0 + q) * kWsFloats + kAOff + e] : 0.f;
+    s_A[i] = (n0 + q < N) ? ws[(size_t)(n0 + q) * kWsHead + kAOff + e] : 0.f;
   }
   __syncthreads();
   const int half = tid >> 7;
@@ -279,8 +281,10 @@ __global__ void __launch_bounds__(256) smpl_skin_kernel(SmplDev m, int n_host, c
   for (int q = 0; q < 16; ++q) {
     const int n = n0 + half * 16 + q;
     if (n >= N) break;
-    const float* vp = ws + (size_t)n * kWsFloats + kWsHead + 3 * v;
-    const float px = vp[0], py = vp[1], pz = vp[2];
+    const float* vp = ws + (size_t)n_host * kWsHead;          // v_posed [81][n_host][256]
+    const int c0 = 3 * v, c1 = c0 + 1, c2 = c0 + 2;
+    const float px = vp[((size_t)(c0 >> 8) * n_host + n) * 256 + (c0 & 255)], py = vp[((size_t)(c1 >> 8) * n_host + n) * 256 + (c1 & 255)],
+                pz = vp[((size_t)(c2 >> 8) * n_host + n) * 256 + (c2 & 255)];
     const float4* A4 = reinterpret_cast<const float4*>(s_A + (half * 16 + q) * 288);
     float4 T0 = make_float4(0.f, 0.f, 0.f, 0.f), T1 = T0, T2 = T0;
 #pragma unroll
@@ -334,7 +338,7 @@ __global__ void __launch_bounds__(256) smpl_joints_kernel(SmplDev m, int n_host,
   if (tid < 3) {
     const float r = (jo[45 * 3 + tid] + jo[46 * 3 + tid]) / 2.f;   // joints54[:,[45,46]].mean(1), smpl.py:104
     s_root[tid] = r;
-    ws[(size_t)n * kWsFloats + kFeatOff + tid] = r;               // feature slots are dead by now
+    ws[(size_t)n * kWsHead + kFeatOff + tid] = r;               // feature slots are dead by now
   }
   __syncthreads();
   for (int i = tid; i < 71 * 3; i += 256) jo[i] -= s_root[i % 3];
@@ -346,7 +350,7 @@ __global__ void __launch_bounds__(256) smpl_root_align_kernel(int n_host, const 
   if (n >= person_count(n_host, d_count)) return;
   const int i = blockIdx.y * 256 + threadIdx.x;
   if (i >= kV * 3) return;
-  verts[(size_t)n * kV * 3 + i] -= ws[(size_t)n * kWsFloats + kFeatOff + (i % 3)];
+  verts[(size_t)n * kV * 3 + i] -= ws[(size_t)n * kWsHead + kFeatOff + (i % 3)];
 }
 
 }  // namespace b200romp
@@ -446,7 +450,7 @@ b200romp_smpl* b200romp_smpl_create(int device, int n_betas, const float* v_temp
   }
   std::vector<float> vt(v_template, v_template + 3 * kV), w(weights, weights + (size_t)kV * kJ);
   // tensor-core blend operands: B'[(v,c)][k'] = [B_hi | B_hi | B_lo] (fp16 hi/lo split of the blend matrix), zero padded
-  std::vector<__half> bq((size_t)kBlendCols * 672, __float2half(0.f));
+  std::vector<__half> bq((size_t)kBlendCols * 448, __float2half(0.f));
   std::vector<float> vtp(kBlendCols, 0.f);
   for (int r = 0; r < 3 * kV; ++r) {
     vtp[r] = v_template[r];
@@ -454,7 +458,7 @@ b200romp_smpl* b200romp_smpl_create(int device, int n_betas, const float* v_temp
       const float b = blend[(size_t)k * 3 * kV + r];
       const __half hi = __float2half_rn(b);
       const __half lo = __float2half_rn(b - __half2float(hi));
-      bq[(size_t)r * 672 + k] = hi; bq[(size_t)r * 672 + 224 + k] = hi; bq[(size_t)r * 672 + 448 + k] = lo;
+      bq[(size_t)r * 448 + k] = hi; bq[(size_t)r * 448 + 224 + k] = lo;
     }
   }
   std::vector<__half> wq((size_t)6912 * 96, __float2half(0.f));
@@ -503,14 +507,15 @@ int b200romp_smpl_forward(b200romp_smpl* s, const float* betas, int betas_stride
   if (simt_blend) {       // round-1 formulation: fp32 FFMA blend + skinning in one SIMT kernel (kept for A/B measurements)
     smpl_verts_kernel<<<grid, 256, s->smem_verts, stream>>>(s->dev, n, d_count, workspace, verts);
   } else {                // shape + pose blend as a tcgen05 GEMM (3-term fp16 split), then skinning on its v_posed
-    int rc = smpl_blend_tc_launch(reinterpret_cast<const char*>(workspace) + kAqOff * sizeof(float), kWsFloats * (int)sizeof(float), n, s->dev.blend_q,
-                                  workspace + kWsHead, s->dev.vt_pad, n, d_count, s->sm_count, stream);
+    float* v_posed = workspace + (size_t)n * kWsHead;            // [81][n][256], after the n records (n = the caller's capacity bound)
+    int rc = smpl_blend_tc_launch(reinterpret_cast<const char*>(workspace) + kAqOff * sizeof(float), kWsHead * (int)sizeof(float), n, s->dev.blend_q,
+                                  v_posed, s->dev.vt_pad, n, d_count, s->sm_count, stream);
     if (rc) return rc;
     static const bool simt_skin = [] { const char* e = getenv("B200ROMP_SMPL_SKIN_SIMT"); return e && e[0] == '1'; }();
     if (simt_skin) {      // FFMA skinning on the blend's v_posed (300 FMA per vertex and person; A/B switch)
       smpl_skin_kernel<<<grid, 256, 0, stream>>>(s->dev, n, d_count, workspace, verts);
     } else {              // skinning as a tiny-K tcgen05 GEMM (smpl_blend_tc.cu: smpl_skin_tc_kernel)
-      rc = smpl_skin_tc_launch(s->dev.skin_w, workspace, kSkinOff * (int)sizeof(float), kWsHead, kWsFloats * (int)sizeof(float), n, n, d_count,
+      rc = smpl_skin_tc_launch(s->dev.skin_w, workspace, kSkinOff * (int)sizeof(float), v_posed, kWsHead * (int)sizeof(float), n, n, d_count,
                                s->sm_count, verts, stream);
       if (rc) return rc;
     }

@@ -28,7 +28,8 @@ for n in (70, 300):
     R = O.batch_rodrigues(torch.from_numpy(thetas).reshape(-1, 3)).reshape(n, 24, 3, 3).numpy().astype(np.float64)
     feat = np.concatenate([betas.astype(np.float64), (R[:, 1:] - np.eye(3)).reshape(n, 207)], 1)
     vp_ref = np.asarray(pack["v_template"], np.float64).reshape(1, -1) + feat @ np.concatenate([S.T, Pd], 0)
-    vp = ws[:, 848:848 + 20670].cpu().double().numpy()
+    # workspace layout (smpl.cu): n records of 1424 floats, then v_posed [81 coordinate tiles][n][256]
+    vp = ws.flatten()[n * 1424:n * 1424 + 81 * n * 256].reshape(81, n, 256).permute(1, 0, 2).reshape(n, 20736)[:, :20670].cpu().double().numpy()
     ev = np.nan_to_num(np.abs(vp - vp_ref), nan=9.0)
     print(f"  v_posed max err {ev.max():.3e}; per-person max (first 12): {np.round(ev.max(1)[:12], 6)}; bad persons {np.nonzero(ev.max(1) > 1e-5)[0][:40]}")
     bc = np.nonzero(ev.max(0) > 1e-5)[0]
