@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define B200ROMP_VERSION 100
+#define B200ROMP_VERSION 200   /* round 2: b200romp_sum_desc.term_c_off, preprocess / temporal / pack entry points */
 
 enum { B200ROMP_OK = 0, B200ROMP_EINVAL = -1, B200ROMP_ECUDA = -2, B200ROMP_ENOMEM = -3, B200ROMP_ESTATE = -4 };
 enum { B200ROMP_F32 = 0, B200ROMP_BF16 = 1, B200ROMP_U8 = 2 };

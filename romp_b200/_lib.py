@@ -160,7 +160,7 @@ def load():
     _sig(lib.b200romp_one_euro_smooth, i32, vp, vp, i32, vp, vp, vp, i32, i32, vp, f32, f32, vp)
     _sig(lib.b200romp_preprocess_bgr, i32, vp, i32, i32, i32, i32, vp, fp, vp)
     _sig(lib.b200romp_pack_rows, i32, C.POINTER(vp), ip, i32, vp, i32, i32, i32, i32, vp, i32, vp)
-    if lib.b200romp_version() != 100:
+    if lib.b200romp_version() != 200:
         raise RuntimeError("libb200romp.so version mismatch - rebuild")
     _lib = lib
     return lib

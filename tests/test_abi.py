@@ -33,7 +33,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_version_and_error_string(lib):
-    assert lib.b200romp_version() == 100
+    assert lib.b200romp_version() == 200
     assert isinstance(lib.b200romp_last_error(), bytes)
 
 
