@@ -421,6 +421,99 @@ __global__ void __launch_bounds__(256, DT == B200ROMP_F32 ? 3 : 4) fuse_sum_pipe
   }
 }
 
+// Ring version with the TERMS in the ring as well (B200ROMP_SUM_RING=1, for terms that are whole tensors): per output row the
+// producer thread bulk-copies the base row and the term row of every term (rows of W/up pixels) into one stage; the compute
+// loop then has no global load at all - in fuse_sum_pipe_kernel every row pays one exposed L2 round trip for its term loads
+// (ncu: long-scoreboard 9 per issue, 2.9 TB/s).
+struct SumRingCfg {
+  int term_bytes[4];     // bytes of one term row
+  int term_off[4];       // byte offset of term k inside a stage
+  int stage_bytes, stages;
+};
+template <int DT>
+__global__ void __launch_bounds__(256) fuse_sum_ring_kernel(const SumParams p, const SumRingCfg cfg, int c8n, int c8_shift, int4 up_shift,
+                                                            int row_bytes) {
+  extern __shared__ uint8_t sum_smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sum_smem_raw) + 127) & ~(uintptr_t)127);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + (size_t)cfg.stages * cfg.stage_bytes);
+  uint64_t* empty = full + cfg.stages;
+  const int ush[4] = {up_shift.x, up_shift.y, up_shift.z, up_shift.w};
+  const int rows = p.B * p.H, per_row = p.W * c8n;
+  const int lane = threadIdx.x & 31;
+  constexpr int ES = DT == B200ROMP_F32 ? 4 : 2;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < cfg.stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], blockDim.x / 32);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  auto fill = [&](int r, int st) {     // thread 0: base row + one row of every term -> stage st
+    const int n = r / p.H, y = r - n * p.H;
+    int total = row_bytes;
+    for (int k = 0; k < p.n_terms; ++k) total += cfg.term_bytes[k];
+    uint8_t* dst = sm + (size_t)st * cfg.stage_bytes;
+    mbar_arrive_expect_tx(&full[st], total);
+    bulk_copy_g2s(dst, reinterpret_cast<const uint8_t*>(p.base) + (size_t)r * row_bytes, row_bytes, &full[st]);
+    for (int k = 0; k < p.n_terms; ++k) {
+      const size_t trow = (size_t)n * (p.H >> ush[k]) + (y >> ush[k]);
+      bulk_copy_g2s(dst + cfg.term_off[k], reinterpret_cast<const uint8_t*>(p.term[k]) + trow * cfg.term_bytes[k], cfg.term_bytes[k], &full[st]);
+    }
+  };
+  if (threadIdx.x == 0)
+    for (int d = 0; d < cfg.stages; ++d) {
+      const int r = blockIdx.x + d * gridDim.x;
+      if (r < rows) fill(r, d);
+    }
+  int iter = 0;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x, ++iter) {
+    const int st = iter % cfg.stages;
+    const uint32_t ph = (uint32_t)(iter / cfg.stages) & 1u;
+    const uint8_t* srow = sm + (size_t)st * cfg.stage_bytes;
+    uint8_t* orow = reinterpret_cast<uint8_t*>(p.out) + (size_t)row * row_bytes;
+    mbar_wait(&full[st], ph);
+    for (int i = threadIdx.x; i < per_row; i += blockDim.x) {
+      const int x = c8_shift >= 0 ? (i >> c8_shift) : i / c8n, c8 = i - x * c8n;
+      float s[8], t[8];
+      sum_load8<DT>(srow, i, s);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < p.n_terms) {
+          sum_load8<DT>(srow + cfg.term_off[k], (uint32_t)((x >> ush[k]) * c8n + c8), t);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s[j] += t[j];         // order: base, term 0, 1, ...
+        }
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] = fmaxf(s[j], 0.f);
+      }
+      if (DT == B200ROMP_F32) {
+        reinterpret_cast<float4*>(orow)[2 * i] = make_float4(s[0], s[1], s[2], s[3]);
+        reinterpret_cast<float4*>(orow)[2 * i + 1] = make_float4(s[4], s[5], s[6], s[7]);
+      } else {
+        uint4 pk;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(s[0], s[1]), h1 = __floats2bfloat162_rn(s[2], s[3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(s[4], s[5]), h3 = __floats2bfloat162_rn(s[6], s[7]);
+        pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+        pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+        reinterpret_cast<uint4*>(orow)[i] = pk;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);
+    if (threadIdx.x == 0) {
+      const int next = row + cfg.stages * gridDim.x;
+      if (next < rows) {
+        mbar_wait(&empty[st], ph);                          // every warp is done with this stage
+        fill(next, st);
+      }
+    }
+  }
+  (void)ES;
+}
+
 int launch_fuse_sum(const SumParams& p, cudaStream_t stream) {
   const int c8n = p.C / 8;
   auto lg = [](int u) { return u == 8 ? 3 : u == 4 ? 2 : u == 2 ? 1 : 0; };
@@ -430,7 +523,43 @@ int launch_fuse_sum(const SumParams& p, cudaStream_t stream) {
   static const bool no_pipe = [] { const char* e = getenv("B200ROMP_SUM_SIMPLE"); return e && e[0] == '1'; }();
   bool same_dt = p.out_dt == p.base_dt;
   for (int k = 0; k < p.n_terms; ++k) same_dt = same_dt && p.term_dt[k] == p.base_dt;
-  if (!no_pipe && same_dt && row_bytes % 16 == 0 && row_bytes <= 16384 && (reinterpret_cast<uintptr_t>(p.base) & 15) == 0 && per_row >= 128) {
+  const bool pipe_ok = !no_pipe && same_dt && row_bytes % 16 == 0 && row_bytes <= 16384 && (reinterpret_cast<uintptr_t>(p.base) & 15) == 0 && per_row >= 128;
+  int c8_shift = -1;
+  for (int b2 = 0; b2 < 8; ++b2) if ((1 << b2) == c8n) c8_shift = b2;
+  static const bool want_ring = [] { const char* e = getenv("B200ROMP_SUM_RING"); return e && e[0] == '1'; }();
+  if (pipe_ok && want_ring) {
+    // every term a whole tensor (no channel slice) whose rows are 16-byte multiples: all operands travel through the ring
+    SumRingCfg cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    bool ok = true;
+    int off = row_bytes;
+    const int es = (int)dtype_size(p.base_dt);
+    for (int k = 0; k < p.n_terms; ++k) {
+      ok = ok && p.term_C[k] == p.C && p.term_c_off[k] == 0 && (reinterpret_cast<uintptr_t>(p.term[k]) & 15) == 0;
+      cfg.term_bytes[k] = (p.W / p.up[k]) * p.C * es;
+      ok = ok && cfg.term_bytes[k] % 16 == 0;
+      cfg.term_off[k] = off;
+      off += cfg.term_bytes[k];
+    }
+    cfg.stage_bytes = (off + 127) / 128 * 128;
+    const int blocks_per_sm = cfg.stage_bytes <= 21 * 1024 ? 3 : 2;
+    cfg.stages = std::min(4, (200 * 1024 / blocks_per_sm - 256) / cfg.stage_bytes);
+    if (ok && cfg.stages >= 2) {
+      const int smem = cfg.stages * cfg.stage_bytes + 2 * cfg.stages * 8 + 128;
+      static bool ring_attr = false;
+      if (!ring_attr) {
+        B2R_CUDA_OK(cudaFuncSetAttribute(fuse_sum_ring_kernel<B200ROMP_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        B2R_CUDA_OK(cudaFuncSetAttribute(fuse_sum_ring_kernel<B200ROMP_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        ring_attr = true;
+      }
+      const int grid = std::min(p.B * p.H, 148 * blocks_per_sm);
+      if (p.base_dt == B200ROMP_F32) fuse_sum_ring_kernel<B200ROMP_F32><<<grid, 256, smem, stream>>>(p, cfg, c8n, c8_shift, sh, row_bytes);
+      else fuse_sum_ring_kernel<B200ROMP_BF16><<<grid, 256, smem, stream>>>(p, cfg, c8n, c8_shift, sh, row_bytes);
+      B2R_CUDA_OK(cudaGetLastError());
+      return B200ROMP_OK;
+    }
+  }
+  if (pipe_ok) {
     const int smem = kSumStages * row_bytes + 2 * kSumStages * 8 + 128;
     static bool attr_done = false;
     if (!attr_done) {
@@ -440,8 +569,6 @@ int launch_fuse_sum(const SumParams& p, cudaStream_t stream) {
     }
     const int blocks_per_sm = row_bytes <= 8192 ? 4 : 3;
     const int grid = std::min(p.B * p.H, 148 * blocks_per_sm);
-    int c8_shift = -1;
-    for (int b2 = 0; b2 < 8; ++b2) if ((1 << b2) == c8n) c8_shift = b2;
     if (p.base_dt == B200ROMP_F32) fuse_sum_pipe_kernel<B200ROMP_F32><<<grid, 256, smem, stream>>>(p, c8n, c8_shift, sh, row_bytes);
     else fuse_sum_pipe_kernel<B200ROMP_BF16><<<grid, 256, smem, stream>>>(p, c8n, c8_shift, sh, row_bytes);
     B2R_CUDA_OK(cudaGetLastError());
